@@ -1,0 +1,391 @@
+// libhlv.so -- kernel (c): classical Gram-Schmidt against a row-major basis resident in HBM,
+// as a bandwidth-bound tall-skinny GEMV pair
+//     project:  c = V w        (rows dot products, ONE streaming pass over V)
+//     update :  w += sign * V^T c  (+ sum w^2 in the same pass, second pass over V)
+// plus the two consumers that are the same memory pattern: the low-rank gradient adjustment
+// (drop-in for the reference's vector_adjust.cu) and Ritz-vector materialisation.
+//
+// Work decomposition ("column owner"): a CTA owns column tiles of kTile consecutive elements;
+// per tile it keeps its slice of w in registers and streams the `rows` basis rows of that tile
+// past it, kRowBatch rows (= 2*kRowBatch independent 128-bit loads per thread) at a time.
+// V is read exactly once per pass, w once (project) or once + one write (update).
+// Arithmetic intensity is 0.5 flop/byte (fp32 basis) -- HBM roofline, no tensor cores.
+#include "hlv_common.cuh"
+
+namespace hlv {
+
+constexpr int kEpt = 8;                         // elements of w per thread per tile
+constexpr int kTile = kThreads * kEpt;          // 2048 columns per tile (8 KB of an fp32 row)
+constexpr int kRowBatch = 8;                    // rows whose loads are in flight together
+
+// ---- per-thread slice of one basis row: 8 consecutive-by-4 elements ---------------------
+// Element layout inside a tile keeps every 128-bit access fully coalesced:
+//   fp32 : vec k (k=0,1) of thread t covers columns  k*1024 + 4t .. +3
+//   bf16 : one 128-bit load of thread t covers columns 8t .. 8t+7
+template <typename BT> struct RowSlice;
+
+template <> struct RowSlice<float> {
+    float4 a, b;
+    static __device__ __forceinline__ int col(int tid, int e) { return (e >> 2) * (kThreads * 4) + tid * 4 + (e & 3); }
+    __device__ __forceinline__ void load(const float* row_tile, int tid) {
+        a = ldg_stream(reinterpret_cast<const float4*>(row_tile) + tid);
+        b = ldg_stream(reinterpret_cast<const float4*>(row_tile) + kThreads + tid);
+    }
+    __device__ __forceinline__ void load_guarded(const float* row_tile, int tid, int64_t valid) {
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { int c = col(tid, e); t[e] = c < valid ? row_tile[c] : 0.0f; }
+        a = make_float4(t[0], t[1], t[2], t[3]); b = make_float4(t[4], t[5], t[6], t[7]);
+    }
+    __device__ __forceinline__ void unpack(float (&x)[8]) const {
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    }
+};
+
+template <> struct RowSlice<uint16_t> {
+    uint4 a;
+    static __device__ __forceinline__ int col(int tid, int e) { return tid * 8 + e; }
+    __device__ __forceinline__ void load(const uint16_t* row_tile, int tid) {
+        a = ldg_stream(reinterpret_cast<const uint4*>(row_tile) + tid);
+    }
+    __device__ __forceinline__ void load_guarded(const uint16_t* row_tile, int tid, int64_t valid) {
+        uint32_t t[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            int c = tid * 8 + 2 * p;
+            uint32_t lo = c < valid ? row_tile[c] : 0u, hi = (c + 1) < valid ? row_tile[c + 1] : 0u;
+            t[p] = lo | (hi << 16);
+        }
+        a = make_uint4(t[0], t[1], t[2], t[3]);
+    }
+    __device__ __forceinline__ void unpack(float (&x)[8]) const {
+        x[0] = bf16_lo(a.x); x[1] = bf16_hi(a.x); x[2] = bf16_lo(a.y); x[3] = bf16_hi(a.y);
+        x[4] = bf16_lo(a.z); x[5] = bf16_hi(a.z); x[6] = bf16_lo(a.w); x[7] = bf16_hi(a.w);
+    }
+};
+
+// w slice of a thread, in the SAME column mapping as RowSlice<BT>.
+template <typename BT>
+__device__ __forceinline__ void load_w(const float* w_tile, int tid, int64_t valid, float (&x)[8]) {
+    if (valid >= kTile) {
+        if (sizeof(BT) == 4) {
+            float4 a = *(reinterpret_cast<const float4*>(w_tile) + tid);
+            float4 b = *(reinterpret_cast<const float4*>(w_tile) + kThreads + tid);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+            float4 a = *(reinterpret_cast<const float4*>(w_tile) + 2 * tid);
+            float4 b = *(reinterpret_cast<const float4*>(w_tile) + 2 * tid + 1);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { int c = RowSlice<BT>::col(tid, e); x[e] = c < valid ? w_tile[c] : 0.0f; }
+    }
+}
+template <typename BT>
+__device__ __forceinline__ void store_w(float* w_tile, int tid, int64_t valid, const float (&x)[8]) {
+    if (valid >= kTile) {
+        float4 a = make_float4(x[0], x[1], x[2], x[3]), b = make_float4(x[4], x[5], x[6], x[7]);
+        if (sizeof(BT) == 4) {
+            *(reinterpret_cast<float4*>(w_tile) + tid) = a;
+            *(reinterpret_cast<float4*>(w_tile) + kThreads + tid) = b;
+        } else {
+            *(reinterpret_cast<float4*>(w_tile) + 2 * tid) = a;
+            *(reinterpret_cast<float4*>(w_tile) + 2 * tid + 1) = b;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { int c = RowSlice<BT>::col(tid, e); if (c < valid) w_tile[c] = x[e]; }
+    }
+}
+
+// =============================================================================
+// project: c[i] = <V_i, w>
+// =============================================================================
+template <typename BT>
+__global__ void __launch_bounds__(kThreads, 2)
+cgs_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const float* __restrict__ w, int64_t n,
+                   double* partials, unsigned* counter, double* c_out) {
+    extern __shared__ double s_acc[];                   // [kWarps][rows_pad]: per-warp running sums
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rows_pad = (rows + kRowBatch - 1) / kRowBatch * kRowBatch;
+    for (int i = tid; i < kWarps * rows_pad; i += kThreads) s_acc[i] = 0.0;
+    __syncthreads();
+    double* my_acc = s_acc + warp * rows_pad;
+    const int my_row = warp_sum8_row(lane);
+    const int64_t ntiles = (n + kTile - 1) / kTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t x0 = tile * kTile;
+        const int64_t valid = n - x0;                   // >= kTile for every tile but a ragged last one
+        float wv[8];
+        load_w<BT>(w + x0, tid, valid, wv);
+        const BT* col0 = V + x0;
+        for (int r0 = 0; r0 < rows; r0 += kRowBatch) {
+            RowSlice<BT> s[kRowBatch];
+#pragma unroll
+            for (int i = 0; i < kRowBatch; ++i) {
+                if (r0 + i < rows) {
+                    const BT* row_tile = col0 + (int64_t)(r0 + i) * ldv;
+                    if (valid >= kTile) s[i].load(row_tile, tid); else s[i].load_guarded(row_tile, tid, valid);
+                }
+            }
+            float p[kRowBatch];
+#pragma unroll
+            for (int i = 0; i < kRowBatch; ++i) {
+                p[i] = 0.0f;
+                if (r0 + i < rows) {
+                    float x[8];
+                    s[i].unpack(x);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) p[i] = fmaf(x[e], wv[e], p[i]);
+                }
+            }
+            const float tot = warp_sum8(p, lane);
+            if ((lane & 3) == 0) my_acc[r0 + my_row] += (double)tot;   // rows_pad covers r0+my_row
+        }
+    }
+    __syncthreads();
+    for (int r = tid; r < rows; r += kThreads) {
+        double t = 0.0;
+#pragma unroll
+        for (int wi = 0; wi < kWarps; ++wi) t += s_acc[wi * rows_pad + r];
+        partials[(size_t)r * kMaxCtas + blockIdx.x] = t;
+    }
+    finalize_rows(partials, counter, rows, c_out);
+}
+
+// =============================================================================
+// update: w += sign * sum_i c[i] V_i ; norm2 = sum w^2
+// =============================================================================
+template <typename BT>
+__global__ void __launch_bounds__(kThreads, 2)
+cgs_update_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const double* __restrict__ c, float sign,
+                  float* __restrict__ w, int64_t n, double* partials, unsigned* counter, double* norm2_out) {
+    extern __shared__ float s_c[];                      // sign * (float)c[i]
+    __shared__ double s_warp[kWarps];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < rows; i += kThreads) s_c[i] = sign * (float)c[i];
+    __syncthreads();
+    float nrm = 0.0f;
+    const int64_t ntiles = (n + kTile - 1) / kTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t x0 = tile * kTile;
+        const int64_t valid = n - x0;
+        float acc[8];
+        load_w<BT>(w + x0, tid, valid, acc);
+        const BT* col0 = V + x0;
+        for (int r0 = 0; r0 < rows; r0 += kRowBatch) {
+            RowSlice<BT> s[kRowBatch];
+#pragma unroll
+            for (int i = 0; i < kRowBatch; ++i) {
+                if (r0 + i < rows) {
+                    const BT* row_tile = col0 + (int64_t)(r0 + i) * ldv;
+                    if (valid >= kTile) s[i].load(row_tile, tid); else s[i].load_guarded(row_tile, tid, valid);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kRowBatch; ++i) {
+                if (r0 + i < rows) {
+                    const float ci = s_c[r0 + i];
+                    float x[8];
+                    s[i].unpack(x);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] = fmaf(ci, x[e], acc[e]);
+                }
+            }
+        }
+        store_w<BT>(w + x0, tid, valid, acc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) nrm = fmaf(acc[e], acc[e], nrm);   // out-of-range slots hold 0
+    }
+    if (norm2_out != nullptr) {
+        double t = block_sum((double)nrm, s_warp);
+        if (tid == 0) partials[blockIdx.x] = t;
+        finalize_rows(partials, counter, 1, norm2_out);
+    }
+}
+
+// coef[i] = (1/eig[i] - 1/(eig[i]+delta)) * dots[i]   (vector_adjust.cu:11, fp32 like the reference)
+__global__ void adjust_coef_kernel(const double* dots, const float* eigvals, float delta, int k, double* coef) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) {
+        float lam = eigvals[i];
+        float s = 1.0f / lam - 1.0f / (lam + delta);
+        coef[i] = (double)(s * (float)dots[i]);
+    }
+}
+
+// =============================================================================
+// Ritz vectors: out[v] = sum_i Y[i, v0+v] Q_i for kNv outputs per pass over Q
+// =============================================================================
+constexpr int kNv = 8;
+constexpr int kRitzBatch = 4;
+
+template <typename BT>
+__global__ void __launch_bounds__(kThreads, 2)
+ritz_vectors_kernel(const BT* __restrict__ Q, int64_t ldq, int m, const float* __restrict__ Y, int ldy,
+                    int v0, int nv, float* __restrict__ out, int64_t ldo, int64_t n) {
+    extern __shared__ float s_y[];                      // [m][kNv]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < m * kNv; i += kThreads) {
+        int r = i / kNv, v = i % kNv;
+        s_y[i] = v < nv ? Y[(int64_t)r * ldy + v0 + v] : 0.0f;
+    }
+    __syncthreads();
+    const int64_t ntiles = (n + kTile - 1) / kTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t x0 = tile * kTile;
+        const int64_t valid = n - x0;
+        float acc[kNv][8];
+#pragma unroll
+        for (int v = 0; v < kNv; ++v)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[v][e] = 0.0f;
+        const BT* col0 = Q + x0;
+        for (int r0 = 0; r0 < m; r0 += kRitzBatch) {
+            RowSlice<BT> s[kRitzBatch];
+#pragma unroll
+            for (int i = 0; i < kRitzBatch; ++i) {
+                if (r0 + i < m) {
+                    const BT* row_tile = col0 + (int64_t)(r0 + i) * ldq;
+                    if (valid >= kTile) s[i].load(row_tile, tid); else s[i].load_guarded(row_tile, tid, valid);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kRitzBatch; ++i) {
+                if (r0 + i < m) {
+                    float x[8];
+                    s[i].unpack(x);
+                    const float4 y0 = *reinterpret_cast<const float4*>(s_y + (r0 + i) * kNv);
+                    const float4 y1 = *reinterpret_cast<const float4*>(s_y + (r0 + i) * kNv + 4);
+                    const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+                    for (int v = 0; v < kNv; ++v)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[v][e] = fmaf(yy[v], x[e], acc[v][e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < kNv; ++v)
+            if (v < nv) store_w<BT>(out + (int64_t)(v0 + v) * ldo + x0, tid, valid, acc[v]);
+    }
+}
+
+// ---- host launchers ---------------------------------------------------------------------
+template <typename BT>
+static int check_basis(const char* name, const BT* V, int64_t ldv, int rows, const float* w, int64_t n) {
+    HLV_REQUIRE(V && w && n >= 0 && rows >= 1 && rows <= HLV_MAX_ROWS, HLV_ERR_ARG,
+                "%s: bad argument (rows=%d, n=%lld)", name, rows, (long long)n);
+    HLV_REQUIRE(ldv >= n, HLV_ERR_ARG, "%s: ldv=%lld < n=%lld", name, (long long)ldv, (long long)n);
+    HLV_REQUIRE(aligned16(V) && aligned16(w) && ((ldv * (int64_t)sizeof(BT)) & 15) == 0, HLV_ERR_ALIGN,
+                "%s: V, w must be 16-byte aligned and ldv*sizeof(elem) a multiple of 16", name);
+    HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "%s: no CUDA device", name);
+    return HLV_OK;
+}
+
+template <typename BT>
+static int project(const char* name, const BT* V, int64_t ldv, int rows, const float* w, int64_t n,
+                   double* c_out, void* ws_raw, size_t ws_bytes, cudaStream_t stream) {
+    int rc = check_basis(name, V, ldv, rows, w, n);
+    if (rc != HLV_OK) return rc;
+    HLV_REQUIRE(c_out != nullptr, HLV_ERR_ARG, "%s: c_out is NULL", name);
+    Workspace ws;
+    HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, rows, &ws), HLV_ERR_WORKSPACE,
+                "%s: workspace too small for %d rows (need %zu bytes)", name, rows, workspace_bytes(rows));
+    const int rows_pad = (rows + kRowBatch - 1) / kRowBatch * kRowBatch;
+    const size_t smem = (size_t)kWarps * rows_pad * sizeof(double);
+    if (smem > 48 * 1024) {                             // only for rows > 768; per-device attribute
+        cudaError_t e = cudaFuncSetAttribute(cgs_project_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kWarps * HLV_MAX_ROWS * (int)sizeof(double));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(project)");
+    }
+    const int grid = persistent_grid((n + kTile - 1) / kTile, 2);
+    cgs_project_kernel<BT><<<grid, kThreads, smem, stream>>>(V, ldv, rows, w, n, ws.partials, ws.counters, c_out);
+    HLV_LAUNCH_CHECK(name);
+    return HLV_OK;
+}
+
+template <typename BT>
+static int update(const char* name, const BT* V, int64_t ldv, int rows, const double* c, float sign, float* w,
+                  int64_t n, double* norm2_out, void* ws_raw, size_t ws_bytes, cudaStream_t stream) {
+    int rc = check_basis(name, V, ldv, rows, w, n);
+    if (rc != HLV_OK) return rc;
+    HLV_REQUIRE(c != nullptr, HLV_ERR_ARG, "%s: c is NULL", name);
+    Workspace ws{};
+    if (norm2_out)
+        HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, 1, &ws), HLV_ERR_WORKSPACE, "%s: workspace too small", name);
+    const int grid = persistent_grid((n + kTile - 1) / kTile, 2);
+    cgs_update_kernel<BT><<<grid, kThreads, rows * sizeof(float), stream>>>(V, ldv, rows, c, sign, w, n, ws.partials,
+                                                                           ws.counters, norm2_out);
+    HLV_LAUNCH_CHECK(name);
+    return HLV_OK;
+}
+
+template <typename BT>
+static int ritz_vectors(const char* name, const BT* Q, int64_t ldq, int m, const float* Y, int ldy, int nvec,
+                        float* out, int64_t ldo, int64_t n, cudaStream_t stream) {
+    HLV_REQUIRE(Q && Y && out && n >= 0 && m >= 1 && m <= HLV_MAX_ROWS && nvec >= 0 && ldy >= nvec, HLV_ERR_ARG,
+                "%s: bad argument", name);
+    HLV_REQUIRE(ldq >= n && ldo >= n, HLV_ERR_ARG, "%s: leading dimension < n", name);
+    HLV_REQUIRE(aligned16(Q) && aligned16(out) && ((ldq * (int64_t)sizeof(BT)) & 15) == 0 && ((ldo * 4) & 15) == 0,
+                HLV_ERR_ALIGN, "%s: Q, out must be 16-byte aligned with 16-byte row pitch", name);
+    HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "%s: no CUDA device", name);
+    const int grid = persistent_grid((n + kTile - 1) / kTile, 2);
+    for (int v0 = 0; v0 < nvec; v0 += kNv) {
+        const int nv = nvec - v0 < kNv ? nvec - v0 : kNv;
+        ritz_vectors_kernel<BT><<<grid, kThreads, (size_t)m * kNv * sizeof(float), stream>>>(Q, ldq, m, Y, ldy, v0, nv,
+                                                                                            out, ldo, n);
+        HLV_LAUNCH_CHECK(name);
+    }
+    return HLV_OK;
+}
+
+}  // namespace hlv
+
+using namespace hlv;
+
+extern "C" {
+
+int hlv_cgs_project_f32(const float* V, int64_t ldv, int rows, const float* w, int64_t n, double* c_out,
+                        void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return project<float>("hlv_cgs_project_f32", V, ldv, rows, w, n, c_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int hlv_cgs_project_bf16(const uint16_t* V, int64_t ldv, int rows, const float* w, int64_t n, double* c_out,
+                         void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return project<uint16_t>("hlv_cgs_project_bf16", V, ldv, rows, w, n, c_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int hlv_cgs_update_f32(const float* V, int64_t ldv, int rows, const double* c, float sign, float* w, int64_t n,
+                       double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return update<float>("hlv_cgs_update_f32", V, ldv, rows, c, sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int hlv_cgs_update_bf16(const uint16_t* V, int64_t ldv, int rows, const double* c, float sign, float* w, int64_t n,
+                        double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return update<uint16_t>("hlv_cgs_update_bf16", V, ldv, rows, c, sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int hlv_vector_adjust_f32(const float* grad_vector, const float* V, const float* eigvals,
+                          float* adjusted_grad_vector, int num_eigenvalues, int64_t vec_len, float delta,
+                          int64_t ldv, double* coef_scratch, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    HLV_REQUIRE(eigvals && coef_scratch && adjusted_grad_vector, HLV_ERR_ARG, "hlv_vector_adjust_f32: bad argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = project<float>("hlv_vector_adjust_f32/project", V, ldv, num_eigenvalues, grad_vector, vec_len,
+                            coef_scratch, ws, ws_bytes, s);
+    if (rc != HLV_OK) return rc;
+    adjust_coef_kernel<<<(num_eigenvalues + 127) / 128, 128, 0, s>>>(coef_scratch, eigvals, delta, num_eigenvalues,
+                                                                     coef_scratch);
+    HLV_LAUNCH_CHECK("hlv_vector_adjust_f32/coef");
+    return update<float>("hlv_vector_adjust_f32/update", V, ldv, num_eigenvalues, coef_scratch, 1.0f,
+                         adjusted_grad_vector, vec_len, nullptr, ws, ws_bytes, s);
+}
+
+int hlv_ritz_vectors_f32(const float* Q, int64_t ldq, int m, const float* Y, int ldy, int nvec, float* out,
+                         int64_t ldo, int64_t n, hlv_stream_t stream) {
+    return ritz_vectors<float>("hlv_ritz_vectors_f32", Q, ldq, m, Y, ldy, nvec, out, ldo, n, static_cast<cudaStream_t>(stream));
+}
+int hlv_ritz_vectors_bf16(const uint16_t* Q, int64_t ldq, int m, const float* Y, int ldy, int nvec, float* out,
+                          int64_t ldo, int64_t n, hlv_stream_t stream) {
+    return ritz_vectors<uint16_t>("hlv_ritz_vectors_bf16", Q, ldq, m, Y, ldy, nvec, out, ldo, n, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+"""Hessian-vector-product operators over a model's flattened parameters.
+
+The HVP itself stays a torch double-backward (BASELINE north star); what this module adds
+around it is the flat-vector plumbing done by libhlv kernels instead of 148 slices,
+444 tiny dot kernels and a torch.cat per application:
+
+  * scatter: ``v`` is sliced into zero-copy per-parameter views (no kernel needed while the
+    flat vector is fp32 and on the parameter device);
+  * second backward as ``autograd.grad(grads, params, grad_outputs=v_views)`` -- the same
+    derivative as the reference's ``sum(v*g).backward()`` (gpt2_hessian_cpu.py:103-106)
+    without materialising the dot;
+  * gather: the per-parameter results go straight into the flat Lanczos vector with
+    ``hlv_gather_f32`` (bit-exact torch.cat replacement, gpt2_hessian_cpu.py:109), accumulated
+    across micro-batches, with alpha = <Hv, v> fused into the last pass.
+
+Operator flavours of the reference that are covered:
+  full model, one batch ............ hess_vec,            gpt2_hessian_cpu.py:75-109
+  full model, dataset average ...... hess_vec,            gpt2_savehessian.py:130-163
+  one transformer block ............ hess_vec_layer,      ipynbs/visual-eigen.ipynb cell 10
+  block-diagonal per tensor ........ hess_vec_layer_by_layer, gpt2_savehessian_layer.py:130-178
+  CIFAR nets (criterion, BN train) . hess_vec,            train_savespec.py:61-91
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Callable, Iterable, List, Optional, Sequence
+
+import torch
+
+
+def lm_loss(model, batch):
+    """``model(input_ids=ids, labels=ids).loss`` -- labels are the inputs, no padding mask
+    (gpt2_hessian_cpu.py:94-97; quirk Q9)."""
+    ids = batch["input_ids"] if isinstance(batch, dict) else batch
+    loss = model(input_ids=ids, labels=ids).loss
+    return loss.mean() if loss.dim() > 0 else loss
+
+
+def criterion_loss(criterion: Callable):
+    """``criterion(model(x), y)`` for (input, target) batches (train_savespec.py:80-81)."""
+    def _loss(model, batch):
+        x, y = batch
+        return criterion(model(x), y)
+    return _loss
+
+
+def _batch_size(batch) -> int:
+    if isinstance(batch, dict):
+        return int(batch["input_ids"].shape[0])
+    if isinstance(batch, (tuple, list)):
+        return int(batch[0].shape[0])
+    return int(batch.shape[0])
+
+
+def _to_device(batch, device, non_blocking=True):
+    if isinstance(batch, dict):
+        return {k: (v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    if isinstance(batch, (tuple, list)):
+        return type(batch)(b.to(device, non_blocking=non_blocking) if torch.is_tensor(b) else b for b in batch)
+    return batch.to(device, non_blocking=non_blocking)
+
+
+def _math_sdpa():
+    """Double-backward needs the MATH scaled-dot-product backend (flash / mem-efficient
+    backward have no derivative)."""
+    try:
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        return sdpa_kernel(SDPBackend.MATH)
+    except Exception:  # pragma: no cover
+        return contextlib.nullcontext()
+
+
+def shard_batches(batches: Sequence, rank: int, world: int) -> List:
+    """Round-robin micro-batch assignment for the batch-sharded HVP (one process per GPU)."""
+    return [b for i, b in enumerate(batches) if i % world == rank]
+
+
+class HessianVectorProduct:
+    """H v for the mean loss over ``batches`` w.r.t. ``params`` (default: all of
+    ``model.parameters()``, the reference's flat order).
+
+    weights[i] multiplies micro-batch i's loss; the default B_i / N reproduces the dataset mean
+    (diego_pythia.py:114, train_savespec.py:82).  With batch sharding pass ``total_sequences`` =
+    the GLOBAL number of sequences so that the sum over ranks is the global mean.
+
+    per_tensor=True gives the block-diagonal-by-tensor operator of gpt2_savehessian_layer.py.
+    cache_graph=True keeps each micro-batch's first-backward graph alive across applications so
+    an application costs only the second backward (memory for speed; the reference rebuilds it).
+    """
+
+    def __init__(self, model: torch.nn.Module, batches: Iterable, loss_fn: Callable = lm_loss,
+                 params: Optional[Sequence[torch.nn.Parameter]] = None,
+                 weights: Optional[Sequence[float]] = None, total_sequences: Optional[int] = None,
+                 per_tensor: bool = False, bn_train_mode: bool = False, cache_graph: bool = False,
+                 device: Optional[torch.device] = None):
+        self.model = model
+        self.params = list(model.parameters()) if params is None else list(params)
+        if not self.params:
+            raise ValueError("no parameters to differentiate")
+        self.device = torch.device(device) if device is not None else self.params[0].device
+        self.numels = [p.numel() for p in self.params]
+        self.n = sum(self.numels)
+        self.batches = list(batches)
+        if not self.batches:
+            raise ValueError("need at least one batch")
+        if weights is None:
+            sizes = [_batch_size(b) for b in self.batches]
+            tot = float(total_sequences if total_sequences is not None else sum(sizes))
+            weights = [s / tot for s in sizes]
+        self.weights = [float(w) for w in weights]
+        self.loss_fn = loss_fn
+        self.per_tensor = per_tensor
+        self.bn_train_mode = bn_train_mode
+        self.cache_graph = cache_graph
+        self._graphs = {}
+        self.applications = 0
+        self.h2d_bytes = 0
+
+    # -- pieces -------------------------------------------------------------------
+    def _views(self, v: torch.Tensor) -> List[torch.Tensor]:
+        v = v.detach().reshape(-1)
+        if v.numel() != self.n:
+            raise ValueError(f"vector has {v.numel()} elements, operator dimension is {self.n}")
+        if v.device != self.device:
+            v = v.to(self.device)                   # reference: .to(param.device), gpt2_hessian_cpu.py:81
+        return [s.view_as(p) for s, p in zip(torch.split(v, self.numels), self.params)]
+
+    def _prepare_model(self):
+        self.model.eval()                           # gpt2_hessian_cpu.py:84
+        if self.bn_train_mode:                      # :85-86
+            for m in self.model.modules():
+                if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                    m.train()
+
+    def _first_backward(self, i: int):
+        if self.cache_graph and i in self._graphs:
+            return self._graphs[i]
+        batch = self.batches[i]
+        probe = batch["input_ids"] if isinstance(batch, dict) else (batch[0] if isinstance(batch, (tuple, list)) else batch)
+        if probe.device != self.device:
+            self.h2d_bytes += sum(t.numel() * t.element_size() for t in
+                                  (batch.values() if isinstance(batch, dict) else (batch if isinstance(batch, (tuple, list)) else [batch]))
+                                  if torch.is_tensor(t))
+            batch = _to_device(batch, self.device)
+        loss = self.loss_fn(self.model, batch) * self.weights[i]
+        grads = torch.autograd.grad(loss, self.params, create_graph=True, allow_unused=True)
+        if self.cache_graph:
+            self._graphs[i] = grads
+        return grads
+
+    def pieces(self, v: torch.Tensor, i: int) -> List[torch.Tensor]:
+        """Per-parameter pieces of (weights[i] * H_i) v for micro-batch i."""
+        views = self._views(v)
+        self._prepare_model()
+        with _math_sdpa():
+            grads = self._first_backward(i)
+            keep = self.cache_graph
+            if not self.per_tensor:
+                used = [(g, p, x) for g, p, x in zip(grads, self.params, views) if g is not None and g.requires_grad]
+                hv = torch.autograd.grad([g for g, _, _ in used], [p for _, p, _ in used],
+                                         grad_outputs=[x for _, _, x in used], retain_graph=keep, allow_unused=True)
+                by_param = {id(p): h for (_, p, _), h in zip(used, hv)}
+                out = [by_param.get(id(p)) for p in self.params]
+            else:
+                out = []
+                last = max((k for k, g in enumerate(grads) if g is not None and g.requires_grad), default=-1)
+                for k, (g, p, x) in enumerate(zip(grads, self.params, views)):
+                    if g is None or not g.requires_grad:
+                        out.append(None)
+                        continue
+                    h = torch.autograd.grad(g, p, grad_outputs=x, retain_graph=keep or k != last, allow_unused=True)[0]
+                    out.append(h)
+        return [h.contiguous() if h is not None else torch.zeros_like(p) for h, p in zip(out, self.params)]
+
+    # -- flat results -----------------------------------------------------------------
+    def accumulate_into(self, v: torch.Tensor, out: torch.Tensor, dot_with=None, dot_out=None,
+                        ws=None, ops=None, phases=None) -> None:
+        """out[:n] = H v (sum over this operator's micro-batches), gathered by libhlv;
+        optionally dot_out = <out, dot_with> fused into the last gather."""
+        if ops is None:
+            from . import kernels as ops
+        nb = len(self.batches)
+        for i in range(nb):
+            pcs = self.pieces(v, i)
+            last = i == nb - 1
+            if phases is not None:
+                phases.start("gather")
+            ops.gather(pcs, out, accumulate=i > 0, dot_with=dot_with if last else None,
+                       dot_out=dot_out if last else None, ws=ws)
+            if phases is not None:
+                phases.stop("gather")
+        self.applications += 1
+
+    def __call__(self, v: torch.Tensor) -> torch.Tensor:
+        """Drop-in ``hess_vec``: flat [P] in -> flat [P] out ([P,1] -> [P,1])."""
+        col = v.dim() == 2
+        out = torch.empty(self.n, dtype=torch.float32, device=self.device)
+        self.accumulate_into(v, out)
+        return out.unsqueeze(1) if col else out
+
+    def clear_cache(self) -> None:
+        self._graphs.clear()
+
+
+class CurvVecProduct:
+    """Same constructor and call shape as the reference's adapter class
+    (gpt2_savehessian.py:166-189): ``CurvVecProduct(loader, model, init_vec=None)``, called with
+    a [P,1] column and returning a [P,1] column ON THE DEVICE (no ``.cpu()``, cf.
+    gpt2_hessian_cpu.py:137 vs gpt2_hessian_gpu.py:137).
+
+    The reference swaps ``init_vec`` in on the first call while gpytorch keeps its own random
+    q_0 (quirk F3).  Here ``init_vec`` is exposed as an attribute and ``lanczos_tridiag`` uses
+    it as the actual start vector, which is what the scripts intend."""
+
+    def __init__(self, loader, model, init_vec: Optional[torch.Tensor] = None, criterion=None,
+                 layer: Optional[torch.nn.Module] = None, **kwargs):
+        loss_fn = criterion_loss(criterion) if criterion is not None else lm_loss
+        params = list(layer.parameters()) if layer is not None else None
+        self.op = HessianVectorProduct(model, loader, loss_fn=loss_fn, params=params, **kwargs)
+        self.init_vec = init_vec
+        self.iters = 0
+
+    @property
+    def n(self) -> int:
+        return self.op.n
+
+    def accumulate_into(self, *a, **k):
+        self.iters += 1
+        return self.op.accumulate_into(*a, **k)
+
+    def __call__(self, vector: torch.Tensor) -> torch.Tensor:
+        self.iters += 1
+        out = self.op(vector.reshape(-1))
+        return out.unsqueeze(1)

@@ -1,0 +1,446 @@
+"""Lanczos tridiagonalisation around a Hessian-vector-product callable, with the
+recurrence, reorthogonalisation and gather running as sm_100a kernels (libhlv).
+
+Public surface (mirrors what the reference scripts hand-roll or get from gpytorch):
+
+    lanczos(hvp, n_iter, v0, reorth=None|'full', ...) -> LanczosResult
+        follows the reference's hand loop (lanczostrain_hand.py:171-203): n_iter = number of
+        HVPs = size of T (the hand loop with lanczos_iters=k corresponds to n_iter=k+1).
+    lanczos_tridiag(matmul_closure, max_iter, dtype, device, matrix_shape, ...) -> (Q[P,m], T[m,m])
+        signature-compatible shim for gpytorch.utils.lanczos.lanczos_tridiag as called at
+        gpt2_hessian_cpu.py:207-213 (full reorthogonalisation, closure sees [P,1]).
+
+Nothing in the loop synchronises with the host: alpha/beta/coefficients live in device
+doubles, kernels read them from there, and T is copied back once at the end (or every
+`check_every` iterations to detect breakdown).  With a process group (`comm`), the basis
+and all vectors are sharded along the parameter dimension: each rank runs the same
+kernels on its shard and the partial scalars are combined with k-float all-reduces.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import ritz as _ritz
+
+_ALIGN = 8          # elements: keeps fp32 and bf16 rows 16-byte aligned
+
+
+# ----------------------------------------------------------------------------
+# process-group wrapper
+# ----------------------------------------------------------------------------
+class Comm:
+    """Thin wrapper over torch.distributed for the three collectives the path needs.
+    ``Comm(None)`` with no initialised process group is the single-process identity."""
+
+    def __init__(self, group=None, enabled: Optional[bool] = None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.group = group
+        on = dist.is_available() and dist.is_initialized() if enabled is None else enabled
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.backend = dist.get_backend(group) if on else "none"
+
+    def all_reduce_sum(self, t: torch.Tensor) -> None:
+        if self.world > 1:
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+
+    def reduce_scatter_sum(self, out: torch.Tensor, full: torch.Tensor) -> None:
+        """out = (sum over ranks of full)[rank*len(out) : (rank+1)*len(out)]"""
+        if self.world == 1:
+            if out.data_ptr() != full.data_ptr():
+                out.copy_(full[: out.numel()])
+            return
+        if self.backend == "gloo":            # gloo has no reduce_scatter: all-reduce and slice
+            self._dist.all_reduce(full, op=self._dist.ReduceOp.SUM, group=self.group)
+            out.copy_(full[self.rank * out.numel(): (self.rank + 1) * out.numel()])
+        else:
+            self._dist.reduce_scatter_tensor(out, full, op=self._dist.ReduceOp.SUM, group=self.group)
+
+    def all_gather(self, full: torch.Tensor, shard: torch.Tensor) -> None:
+        if self.world == 1:
+            if full.data_ptr() != shard.data_ptr():
+                full[: shard.numel()].copy_(shard)
+            return
+        self._dist.all_gather_into_tensor(full, shard, group=self.group)
+
+    def barrier(self) -> None:
+        if self.world > 1:
+            self._dist.barrier(group=self.group)
+
+
+# ----------------------------------------------------------------------------
+# CUDA-event phase timer (optional)
+# ----------------------------------------------------------------------------
+class _Phases:
+    def __init__(self, enabled: bool):
+        self.enabled = enabled
+        self.pairs: List[Tuple[str, int, Any, Any]] = []
+        self._open: Dict[str, Any] = {}
+
+    def start(self, name: str) -> None:
+        if self.enabled:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._open[name] = e
+
+    def stop(self, name: str, rows: int = 0) -> None:
+        if self.enabled:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.pairs.append((name, rows, self._open.pop(name), e))
+
+    def summary(self) -> Dict[str, Dict[str, float]]:
+        out: Dict[str, Dict[str, float]] = {}
+        if not self.enabled:
+            return out
+        torch.cuda.synchronize()
+        for name, rows, a, b in self.pairs:
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0, "rows": 0})
+            d["ms"] += a.elapsed_time(b)
+            d["calls"] += 1
+            d["rows"] += rows
+        return out
+
+
+# ----------------------------------------------------------------------------
+# result
+# ----------------------------------------------------------------------------
+@dataclass
+class LanczosResult:
+    """Outcome of a Lanczos run.
+
+    alphas[j] = T[j,j]; betas[j] = T[j,j+1] for j < m-1 and betas[m-1] is the final residual
+    norm.  eigvals (ascending) / gammas follow gpt2_hessian_cpu.py:215-216.  ``basis`` holds the
+    Lanczos vectors as ROWS (the hand loop's Q, lanczostrain_hand.py:176) on the device, local
+    shard only when the run was sharded."""
+    alphas: torch.Tensor
+    betas: torch.Tensor
+    eigvals: torch.Tensor
+    gammas: torch.Tensor
+    Y: np.ndarray
+    m: int
+    n: int
+    breakdown: bool = False
+    basis: Optional[torch.Tensor] = None
+    n_local: int = 0
+    timings: Dict[str, Dict[str, float]] = field(default_factory=dict)
+    _ops: Any = None
+
+    @property
+    def T(self) -> torch.Tensor:
+        return _ritz.dense_T(self.alphas.numpy(), self.betas.numpy())
+
+    @property
+    def Q(self) -> torch.Tensor:
+        """[m, n_local] rows = Lanczos vectors (view into the device basis)."""
+        if self.basis is None:
+            raise RuntimeError("this run did not keep its basis (keep_basis=False)")
+        return self.basis[: self.m, : self.n_local]
+
+    def ritz_vectors(self, which: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """Rows = Ritz vectors  V = Y^T Q  (gpt2_hessian_cpu.py:217) for the eigenvalue indices in
+        ``which`` (indices into the ascending ``eigvals``; default all), as a device fp32
+        [len(which), n_local] tensor.  Streams the basis once per 8 requested vectors."""
+        if self.basis is None:
+            raise RuntimeError("this run did not keep its basis (keep_basis=False)")
+        idx = list(range(self.m)) if which is None else [int(i) % self.m for i in which]
+        dev = self.basis.device
+        Ysel = torch.from_numpy(np.ascontiguousarray(self.Y[:, idx])).to(torch.float32).to(dev).contiguous()
+        ld = (self.n_local + _ALIGN - 1) // _ALIGN * _ALIGN
+        out = torch.empty(len(idx), ld, dtype=torch.float32, device=dev)
+        self._ops.ritz_vectors(self.basis, self.m, Ysel, out, self.n_local)
+        return out[:, : self.n_local]
+
+    def eigeninfo(self, basis: bool = False) -> Dict[str, torch.Tensor]:
+        """The reference's result dict (gpt2_savehessian.py:216-223; 'V' as train_savespec.py:328-333)."""
+        d = {"eigvals": self.eigvals.clone(), "gammas": self.gammas.clone()}
+        if basis:
+            d["V"] = self.ritz_vectors()
+        return d
+
+
+# ----------------------------------------------------------------------------
+# engine
+# ----------------------------------------------------------------------------
+class LanczosEngine:
+    """Device-resident state of one Lanczos run; ``step(j)`` performs iteration j."""
+
+    def __init__(self, hvp: Callable, n: int, n_iter: int, device, reorth: Optional[str] = None,
+                 basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
+                 breakdown_tol: Optional[float] = None, comm: Optional[Comm] = None, ops=None,
+                 profile: bool = False, column_vectors: bool = False, cgs_passes: int = 2):
+        if reorth not in (None, "full"):
+            raise ValueError("reorth must be None or 'full'")
+        if basis_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("basis_dtype must be torch.float32 or torch.bfloat16")
+        if n_iter < 1:
+            raise ValueError("n_iter must be >= 1")
+        if ops is None:
+            from . import kernels as ops      # the CUDA library; raises if it is not built
+        self.ops = ops
+        self.hvp = hvp
+        self.n, self.m = int(n), int(n_iter)
+        self.device = torch.device(device)
+        self.reorth = reorth
+        self.cgs_passes = int(cgs_passes)
+        self.basis_dtype = basis_dtype
+        self.keep_basis = (reorth == "full") if keep_basis is None else bool(keep_basis or reorth == "full")
+        self.breakdown_tol = (1e-6 if reorth == "full" else 0.0) if breakdown_tol is None else float(breakdown_tol)
+        self.comm = comm if comm is not None else Comm(enabled=False)
+        self.column_vectors = column_vectors
+        self.phases = _Phases(profile)
+        G = self.comm.world
+        self.shard_n = (-(-self.n // G) + _ALIGN - 1) // _ALIGN * _ALIGN      # per-rank length (zero padded)
+        self.n_pad = self.shard_n * G
+        self.lo = self.comm.rank * self.shard_n
+        f32, f64 = dict(dtype=torch.float32, device=self.device), dict(dtype=torch.float64, device=self.device)
+        sn, m = self.shard_n, self.m
+        # --- basis and current/previous vectors (local shard) ---
+        self.basis = None
+        self.fp32_rows = self.keep_basis and basis_dtype == torch.float32
+        if self.keep_basis:
+            self.basis = torch.zeros(m, sn, dtype=basis_dtype, device=self.device)
+        if not self.fp32_rows:
+            self.ring = [torch.zeros(sn, **f32) for _ in range(2)]
+        # --- full-length buffers (only distinct from the shard when sharded) ---
+        if G > 1:
+            self.v_full = torch.zeros(self.n_pad, **f32)
+            self.hv_full = torch.zeros(self.n_pad, **f32)
+            self.w = torch.zeros(sn, **f32)
+        else:
+            self.v_full = None
+            self.hv_full = None
+            self.w = torch.zeros(sn, **f32)
+        # --- device scalars ---
+        self.alphas = torch.zeros(m, **f64)
+        self.betas = torch.zeros(m + 1, **f64)          # betas[j+1] = ||w|| after iteration j; betas[0] unused
+        self.norm2 = torch.zeros(1, **f64)
+        self.coef = torch.zeros(max(m, 1), **f64)
+        self.breakdown_iter = torch.full((1,), -1, dtype=torch.int32, device=self.device)
+        self.ws = ops.Workspace(self.device, max_rows=max(m, 1))
+        self.j = 0
+        self.launches = 0
+
+    # -- vectors ---------------------------------------------------------------
+    def _v_shard(self, j: int) -> torch.Tensor:
+        return self.basis[j] if self.fp32_rows else self.ring[j & 1]
+
+    def _v_for_hvp(self, j: int) -> torch.Tensor:
+        v = self.v_full if self.comm.world > 1 else self._v_shard(j)
+        v = v[: self.n]
+        return v.unsqueeze(1) if self.column_vectors else v
+
+    def start(self, v0: torch.Tensor, normalize: bool = False) -> None:
+        """Install the start vector (global, length n).  The hand loop assumes ||v0|| = 1
+        (lanczostrain_hand.py:162-163 normalises before the loop)."""
+        v0 = v0.reshape(-1)
+        if v0.numel() != self.n:
+            raise ValueError(f"v0 has {v0.numel()} elements, operator dimension is {self.n}")
+        v0 = v0.to(device=self.device, dtype=torch.float32)
+        if normalize:
+            v0 = v0 / torch.linalg.vector_norm(v0)
+        self.j = 0
+        self.alphas.zero_(); self.betas.zero_(); self.breakdown_iter.fill_(-1)
+        local = torch.zeros(self.shard_n, dtype=torch.float32, device=self.device)
+        hi = min(self.lo + self.shard_n, self.n)
+        if hi > self.lo:
+            local[: hi - self.lo] = v0[self.lo: hi]
+        if self.fp32_rows:
+            self.basis[0].copy_(local)
+        else:
+            self.ring[0].copy_(local)
+            if self.keep_basis:
+                self.basis[0].copy_(local.to(self.basis_dtype))
+        if self.comm.world > 1:
+            self.v_full.zero_()
+            self.v_full[: self.n].copy_(v0)
+
+    # -- one operator application: fills self.w (local shard of H v_j) and alphas[j] ------
+    def _apply(self, j: int) -> None:
+        ops, G, n = self.ops, self.comm.world, self.n
+        v_in = self._v_for_hvp(j)
+        v_sh = self._v_shard(j)
+        a_out = self.alphas[j: j + 1]
+        ph = self.phases
+        fused_dot = G == 1
+        target = self.w if G == 1 else self.hv_full
+        tgt = target[:n] if target.numel() != n else target
+        ph.start("hvp")
+        if hasattr(self.hvp, "accumulate_into"):
+            # library operator: runs the double-backward per micro-batch and gathers the per-tensor
+            # pieces straight into the flat vector (fused alpha on the last micro-batch)
+            self.hvp.accumulate_into(v_in, tgt, dot_with=v_sh[:n] if fused_dot else None,
+                                     dot_out=a_out if fused_dot else None, ws=self.ws, ops=ops, phases=ph)
+            ph.stop("hvp")
+            need_dot = not fused_dot
+        else:
+            r = self.hvp(v_in)
+            ph.stop("hvp")
+            if isinstance(r, (list, tuple)):
+                ph.start("gather")
+                ops.gather(list(r), tgt, dot_with=v_sh[:n] if fused_dot else None,
+                           dot_out=a_out if fused_dot else None, ws=self.ws)
+                ph.stop("gather")
+                need_dot = not fused_dot
+            else:
+                r = r.detach().reshape(-1)
+                if r.numel() != n:
+                    raise ValueError(f"hvp returned {r.numel()} elements, expected {n}")
+                if r.device != self.device or r.dtype != torch.float32:
+                    r = r.to(device=self.device, dtype=torch.float32)    # slow path (e.g. a closure that ends in .cpu())
+                if G == 1 and n == self.shard_n and r.is_contiguous() and r.data_ptr() % 16 == 0:
+                    self.w = r                                           # adopt the fresh tensor, no copy
+                else:
+                    tgt.copy_(r)
+                need_dot = True
+        if G > 1:
+            ph.start("reduce_scatter")
+            self.comm.reduce_scatter_sum(self.w, self.hv_full)
+            ph.stop("reduce_scatter")
+        if need_dot:
+            ph.start("dot")
+            ops.dot(self.w, v_sh, a_out, self.ws)
+            ph.stop("dot")
+            self.comm.all_reduce_sum(a_out)
+
+    def step(self, j: Optional[int] = None, store_next: bool = True) -> None:
+        """Iteration j of the hand loop (lanczostrain_hand.py:188-203 order):
+        w = H v_j; alpha_j = w.v_j; w -= alpha_j v_j + beta_j v_{j-1}; [CGS2 vs rows 0..j];
+        beta_{j+1} = ||w||; v_{j+1} = w / beta_{j+1}."""
+        j = self.j if j is None else j
+        ops, ph, comm = self.ops, self.phases, self.comm
+        self._apply(j)
+        v_j = self._v_shard(j)
+        ph.start("update")
+        if j == 0:
+            ops.lanczos_update(self.w, v_j, None, self.alphas[j: j + 1], None, self.norm2, self.ws)
+        else:
+            ops.lanczos_update(self.w, v_j, self._v_shard(j - 1), self.alphas[j: j + 1],
+                               self.betas[j: j + 1], self.norm2, self.ws)
+        ph.stop("update")
+        if self.reorth == "full":
+            rows = j + 1
+            for _ in range(self.cgs_passes):
+                ph.start("cgs_project")
+                ops.cgs_project(self.basis, rows, self.w, self.coef, self.ws)
+                ph.stop("cgs_project", rows)
+                comm.all_reduce_sum(self.coef[:rows])
+                ph.start("cgs_update")
+                ops.cgs_update(self.basis, rows, self.coef, self.w, self.norm2, self.ws)
+                ph.stop("cgs_update", rows)
+        comm.all_reduce_sum(self.norm2)
+        if store_next:
+            ph.start("normalize")
+            nxt = j + 1
+            if nxt < self.m:
+                v_out = self.basis[nxt] if self.fp32_rows else self.ring[nxt & 1]
+                row16 = self.basis[nxt] if (self.keep_basis and not self.fp32_rows) else None
+            else:                       # last iteration: only beta_m (residual norm) is needed
+                v_out, row16 = None, None
+            ops.normalize_store(self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16,
+                                self.breakdown_tol, self.breakdown_iter, j)
+            ph.stop("normalize")
+            if comm.world > 1 and nxt < self.m:
+                ph.start("all_gather")
+                comm.all_gather(self.v_full, v_out)
+                ph.stop("all_gather")
+        self.j = j + 1
+
+    # -- host read-back -----------------------------------------------------------
+    def broke_down(self) -> int:
+        """Iteration index at which beta fell below breakdown_tol, or -1 (synchronises)."""
+        return int(self.breakdown_iter.item())
+
+    def tridiagonal(self, upto: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """(alphas[:k], betas[:k]) computed so far as float64 numpy (synchronises)."""
+        k = self.j if upto is None else upto
+        a = self.alphas[:k].cpu().numpy().copy()
+        b = self.betas[1: k + 1].cpu().numpy().copy()
+        return a, b
+
+    def result(self) -> LanczosResult:
+        bd = self.broke_down()
+        m_eff = self.j if bd < 0 else min(self.j, bd + 1)
+        a, b = self.tridiagonal(m_eff)
+        # fp32 round trip: T is an fp32 matrix in the reference
+        a32, b32 = a.astype(np.float32), b.astype(np.float32)
+        eigvals, gammas, Y = _ritz.ritz_values(a32, b32)
+        return LanczosResult(alphas=torch.from_numpy(a32.astype(np.float64)), betas=torch.from_numpy(b32.astype(np.float64)),
+                             eigvals=eigvals, gammas=gammas, Y=Y, m=m_eff, n=self.n, breakdown=bd >= 0,
+                             basis=self.basis if self.keep_basis else None, n_local=self.shard_n if self.comm.world > 1 else self.n,
+                             timings=self.phases.summary(), _ops=self.ops)
+
+
+def lanczos(hvp: Callable, n_iter: int, v0: torch.Tensor, reorth: Optional[str] = None, *,
+            basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
+            breakdown_tol: Optional[float] = None, check_every: int = 16, normalize_v0: bool = False,
+            comm: Optional[Comm] = None, ops=None, profile: bool = False, column_vectors: bool = False,
+            on_iteration: Optional[Callable[[int, LanczosEngine], None]] = None) -> LanczosResult:
+    """Run ``n_iter`` Lanczos iterations of the symmetric operator ``hvp`` from ``v0``.
+
+    hvp: callable v[P] -> Hv.  It may return a flat [P] (or [P,1]) tensor, or -- to use the fused
+         gather + alpha kernel -- the list of per-parameter pieces in ``model.parameters()``
+         order (what ``torch.autograd.grad`` returns), or be a library operator
+         (``hvp.HessianVectorProduct``).
+    reorth: None = the reference hand loop (lanczostrain_hand.py:171-203);
+            'full' = hand-loop order + two-pass classical Gram-Schmidt against all stored rows.
+    v0 must have unit norm (pass normalize_v0=True otherwise), as in the reference.
+    """
+    dev = v0.device
+    if dev.type != "cuda" and ops is None:
+        raise RuntimeError("lanczos: v0 must live on a CUDA device; this engine has no CPU path")
+    eng = LanczosEngine(hvp, v0.numel(), n_iter, dev, reorth=reorth, basis_dtype=basis_dtype,
+                        keep_basis=keep_basis, breakdown_tol=breakdown_tol, comm=comm, ops=ops,
+                        profile=profile, column_vectors=column_vectors)
+    eng.start(v0, normalize=normalize_v0)
+    for j in range(n_iter):
+        eng.step(j)
+        if on_iteration is not None:
+            on_iteration(j, eng)
+        if eng.breakdown_tol > 0 and check_every > 0 and (j + 1) % check_every == 0 and j + 1 < n_iter:
+            if eng.broke_down() >= 0:
+                break
+    return eng.result()
+
+
+def lanczos_tridiag(matmul_closure: Callable, max_iter: int, dtype=torch.float32, device="cuda",
+                    matrix_shape=None, batch_shape=None, init_vecs: Optional[torch.Tensor] = None,
+                    num_init_vecs: int = 1, tol: float = 1e-5, **engine_kwargs):
+    """Drop-in for ``gpytorch.utils.lanczos.lanczos_tridiag`` as the reference calls it
+    (gpt2_hessian_cpu.py:207-213, gpt2_savehessian.py:202-208): returns ``(Q[P,m], T[m,m])`` with
+    full reorthogonalisation, calling ``matmul_closure`` with [P,1] column vectors.
+
+    Differences, all documented in INTEGRATION.md: the recurrence always runs on the current
+    CUDA device (``device='cpu'`` only moves the RESULTS to the host, as gpt2_hessian_cpu.py
+    expects); a single probe vector (num_init_vecs=1, no batch_shape) is supported; ``init_vecs``
+    defaults to randn(P,1) and is normalised, exactly like gpytorch -- the reference's
+    ``init_vec`` swap inside CurvVecProduct (quirk F3) is therefore not needed: pass init_vecs."""
+    if dtype != torch.float32:
+        raise NotImplementedError("lanczos_tridiag: only float32 (the reference's dtype) is supported")
+    if num_init_vecs != 1 or (batch_shape is not None and len(tuple(batch_shape)) > 0):
+        raise NotImplementedError("lanczos_tridiag: a single probe vector is supported")
+    if matrix_shape is None:
+        raise ValueError("matrix_shape is required")
+    P = int(tuple(matrix_shape)[-1])
+    if init_vecs is None and getattr(matmul_closure, "init_vec", None) is not None:
+        init_vecs = matmul_closure.init_vec          # CurvVecProduct(loader, model, init_vec=...) -- see hvp.py
+    if torch.device(device).type == "cuda":
+        cuda_dev = torch.device(device)
+    elif engine_kwargs.get("ops") is not None and init_vecs is not None:
+        cuda_dev = init_vecs.device                  # test double: stay where the caller's data is
+    else:
+        cuda_dev = torch.device("cuda", torch.cuda.current_device())
+    if init_vecs is None:
+        init_vecs = torch.randn(P, 1, dtype=torch.float32, device=cuda_dev)
+    res = lanczos(matmul_closure, max_iter, init_vecs.reshape(-1).to(cuda_dev), reorth="full",
+                  normalize_v0=True, column_vectors=True, breakdown_tol=1e-6, **engine_kwargs)
+    Q = res.Q.t()                       # [P, m] view of the row-major device basis
+    T = res.T
+    out_dev = torch.device(device)
+    return Q.to(out_dev), T.to(out_dev)

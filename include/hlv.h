@@ -1,0 +1,143 @@
+/*
+ * hlv.h -- C ABI of libhlv.so: the B200 (sm_100a) kernels of the Lanczos /
+ * stochastic-Lanczos-quadrature recurrence hot path.
+ *
+ * Boundary being replaced.  The reference's only native code is the bare kernel
+ *   extern "C" __global__ void vector_adjust(const float* grad_vector, const float* V,
+ *        const float* eigvals, float* adjusted_grad_vector, int num_eigenvalues,
+ *        int vec_len, float delta)                       (vector_adjust.cu:2)
+ * built with `nvcc --shared -o vector_adjust.so --compiler-options '-fPIC'`
+ * (shared_kernel:1) and launched from Python through pycuda with raw device
+ * pointers of caller-owned, row-major contiguous torch CUDA tensors
+ * (gpt_hessian_cuda.py:25-54).  Everything else on the path is stock torch ops
+ * (torch.cat / dot / norm / axpy, and the reorth loop inside gpytorch).  This
+ * header keeps that contract -- raw device pointers, caller-owned buffers,
+ * row-major fp32, nothing allocated by the library -- and adds what the
+ * reference lacks: HOST entry points (not bare kernels), a stream argument, and
+ * an error convention.
+ *
+ * Conventions (every function):
+ *   - returns HLV_OK (0) or a negative HLV_ERR_* code; never throws, never
+ *     synchronises the device, never allocates device memory;
+ *   - all pointers are DEVICE pointers unless the parameter name starts with
+ *     `h_` (host arrays that are consumed before the call returns);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     work is stream-ordered;
+ *   - scalar results (dot products, squared norms, Gram-Schmidt coefficients)
+ *     are written to caller-provided DEVICE doubles: they are fp32 per-thread
+ *     FMA chains combined in a fixed order with an fp64 final stage, so a result
+ *     depends only on (n, launch geometry), never on block scheduling;
+ *   - `ws` is a scratch buffer of at least hlv_workspace_bytes(max_rows) bytes
+ *     that must be zeroed ONCE (hlv_workspace_init) and must not be shared by
+ *     calls running concurrently on different streams;
+ *   - vectors of length n: base pointers 16-byte aligned; basis rows are
+ *     row-major with leading dimension `ldv` elements, ldv*sizeof(elem) % 16 == 0.
+ *     n itself is arbitrary (ragged tails are handled in-kernel).
+ */
+#ifndef HLV_H_
+#define HLV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HLV_VERSION 100            /* 0.1.0 */
+
+#define HLV_OK              0
+#define HLV_ERR_ARG        -1      /* null pointer / negative size / rows out of range */
+#define HLV_ERR_ALIGN      -2      /* pointer or leading dimension not 16-byte aligned */
+#define HLV_ERR_WORKSPACE  -3      /* ws too small */
+#define HLV_ERR_CUDA       -4      /* CUDA runtime error; see hlv_last_error_string() */
+#define HLV_ERR_NO_DEVICE  -5      /* no CUDA device / not sm_100 */
+
+#define HLV_MAX_ROWS      1024     /* max basis rows per project/update call */
+#define HLV_MAX_TENSORS   1024     /* max tensors per gather/scatter launch (longer lists are chunked) */
+
+typedef void* hlv_stream_t;
+
+/* ---- library ------------------------------------------------------------ */
+int         hlv_version(void);
+const char* hlv_last_error_string(void);                 /* thread-local, never NULL */
+/* sm count / compute capability of the current device (cached). */
+int         hlv_device_info(int* sm_count, int* cc_major, int* cc_minor);
+size_t      hlv_workspace_bytes(int max_rows);
+int         hlv_workspace_init(void* ws, size_t ws_bytes, hlv_stream_t stream);
+
+/* ---- (a) gather / scatter between per-tensor buffers and the flat vector -- */
+/* Replaces torch.cat([p.grad.view(-1) ...]) (gpt2_hessian_cpu.py:109,200) and the
+ * slice/split of :79-82,:231-233.  dst[off_t + i] = src_t[i] in list order.
+ *   scale/accumulate: dst = (accumulate ? dst : 0) + scale*src.  With scale==1 and
+ *   accumulate==0 the copy is bit-exact (no arithmetic is performed).
+ *   v, dot_out (both NULL or both set): also writes dot_out[0] = sum_i dst_new[i]*v[i]
+ *   (the Lanczos alpha, lanczostrain_hand.py:200) in the same pass.
+ *   h_src[t] are device pointers to contiguous fp32 tensors of h_numel[t] elements. */
+int hlv_gather_f32(const void* const* h_src, const int64_t* h_numel, int ntensors,
+                   float* dst, int64_t dst_len, float scale, int accumulate,
+                   const float* v, double* dot_out,
+                   void* ws, size_t ws_bytes, hlv_stream_t stream);
+/* dst_t[i] = src[off_t + i]  (bit-exact). */
+int hlv_scatter_f32(const float* src, int64_t src_len,
+                    void* const* h_dst, const int64_t* h_numel, int ntensors,
+                    hlv_stream_t stream);
+
+/* ---- (b) recurrence -------------------------------------------------------- */
+/* out[0] = sum a[i]*b[i]   (torch.dot, lanczostrain_hand.py:183,200) */
+int hlv_dot_f32(const float* a, const float* b, int64_t n, double* out,
+                void* ws, size_t ws_bytes, hlv_stream_t stream);
+/* w -= alpha*vj + beta*vjm1 and norm2_out[0] = sum w_new^2, one pass
+ * (lanczostrain_hand.py:202 fused with :190).  alpha/beta are device doubles,
+ * rounded to fp32 before use; vjm1/beta may be NULL (first iteration, :185). */
+int hlv_lanczos_update_f32(float* w, const float* vj, const float* vjm1,
+                           const double* alpha, const double* beta, int64_t n,
+                           double* norm2_out,
+                           void* ws, size_t ws_bytes, hlv_stream_t stream);
+/* beta = sqrt(norm2[0]); beta_out[0] = beta; v_out = w / beta (lanczostrain_hand.py:190-194).
+ * row_bf16 (optional) additionally receives the bf16-rounded copy (bf16 basis storage);
+ * v_out may be NULL (bf16 row only); with both NULL only beta_out is written.  v_out != w.
+ * If beta < breakdown_tol and *breakdown_iter < 0, *breakdown_iter = iter. */
+int hlv_normalize_store_f32(const float* w, const double* norm2, int64_t n,
+                            double* beta_out, float* v_out, uint16_t* row_bf16,
+                            double breakdown_tol, int* breakdown_iter, int iter,
+                            hlv_stream_t stream);
+
+/* ---- (c) classical Gram-Schmidt against a row-major basis in HBM ----------- */
+/* c_out[i] = sum_x V[i*ldv + x] * w[x],  i < rows      (one streaming pass over V) */
+int hlv_cgs_project_f32 (const float*    V, int64_t ldv, int rows, const float* w, int64_t n,
+                         double* c_out, void* ws, size_t ws_bytes, hlv_stream_t stream);
+int hlv_cgs_project_bf16(const uint16_t* V, int64_t ldv, int rows, const float* w, int64_t n,
+                         double* c_out, void* ws, size_t ws_bytes, hlv_stream_t stream);
+/* w[x] += sign * sum_i c[i] * V[i*ldv + x]; norm2_out[0] = sum w_new^2 (may be NULL).
+ * c are device doubles, rounded to fp32 before use.  sign = -1 for reorthogonalisation. */
+int hlv_cgs_update_f32 (const float*    V, int64_t ldv, int rows, const double* c, float sign,
+                        float* w, int64_t n, double* norm2_out,
+                        void* ws, size_t ws_bytes, hlv_stream_t stream);
+int hlv_cgs_update_bf16(const uint16_t* V, int64_t ldv, int rows, const double* c, float sign,
+                        float* w, int64_t n, double* norm2_out,
+                        void* ws, size_t ws_bytes, hlv_stream_t stream);
+
+/* ---- low-rank gradient adjustment: drop-in for vector_adjust.cu:2-15 -------- */
+/* adjusted[x] += sum_i (1/eig[i] - 1/(eig[i]+delta)) * (grad . V_i) * V[i*ldv + x].
+ * Same argument meaning and order as the reference kernel (+ ldv, scratch, stream);
+ * two streaming passes over V instead of the reference's O(k*n^2) loads.
+ * coef_scratch: device doubles, >= num_eigenvalues. */
+int hlv_vector_adjust_f32(const float* grad_vector, const float* V, const float* eigvals,
+                          float* adjusted_grad_vector, int num_eigenvalues, int64_t vec_len,
+                          float delta, int64_t ldv, double* coef_scratch,
+                          void* ws, size_t ws_bytes, hlv_stream_t stream);
+
+/* ---- Ritz vectors: out[r*ldo + x] = sum_i Y[i*ldy + r] * Q[i*ldq + x] --------
+ * (V = eigvects.t() @ Q, gpt2_hessian_cpu.py:217 / lanczostrain_hand.py:210)
+ * Y is a DEVICE fp32 m x ldy matrix whose columns are eigenvectors of T; the
+ * first `nvec` columns are materialised. */
+int hlv_ritz_vectors_f32 (const float*    Q, int64_t ldq, int m, const float* Y, int ldy, int nvec,
+                          float* out, int64_t ldo, int64_t n, hlv_stream_t stream);
+int hlv_ritz_vectors_bf16(const uint16_t* Q, int64_t ldq, int m, const float* Y, int ldy, int nvec,
+                          float* out, int64_t ldo, int64_t n, hlv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLV_H_ */

@@ -1,0 +1,235 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/hlv.h declares; argument
+validation that returns before any CUDA work; host logic (Ritz, result layout, engine control
+flow with the oracle-backed test double, 2-rank gloo sharding)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests import fake_ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- C ABI
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "hlv.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(hlv_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(libhlv):
+    from hessian_llm_vision_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(libhlv, n), f"{n} declared in hlv.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (hlv_\w+)", out))
+    assert exported == set(names)             # nothing undeclared leaks out either
+
+
+def test_library_is_sm100a_with_lineinfo(libhlv):
+    from hessian_llm_vision_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_version_workspace_and_arg_errors(libhlv):
+    assert libhlv.hlv_version() == 100
+    assert libhlv.hlv_workspace_bytes(1) >= 256 + 2048 * 8
+    assert libhlv.hlv_workspace_bytes(100) - libhlv.hlv_workspace_bytes(99) == 2048 * 8
+    # argument validation happens before any device work -> safe without a GPU
+    assert libhlv.hlv_dot_f32(None, None, 16, None, None, 0, None) == -1
+    assert b"hlv_dot_f32" in libhlv.hlv_last_error_string()
+    assert libhlv.hlv_cgs_project_f32(None, 8, 1, None, 8, None, None, 0, None) == -1
+    assert libhlv.hlv_cgs_project_f32(16, 8, 2000, 32, 8, 48, None, 0, None) == -1     # rows > HLV_MAX_ROWS
+    assert libhlv.hlv_cgs_project_f32(16, 4, 1, 32, 8, 48, None, 0, None) == -1        # ldv < n
+    assert libhlv.hlv_cgs_project_f32(20, 8, 1, 32, 8, 48, None, 0, None) == -2        # misaligned V
+    assert libhlv.hlv_cgs_project_bf16(16, 12, 1, 32, 8, 48, None, 0, None) == -2      # bf16 ldv*2 % 16 != 0
+    assert libhlv.hlv_workspace_init(None, 0, None) == -1
+    numel = (C.c_int64 * 1)(4)
+    ptrs = (C.c_void_p * 1)(64)
+    assert libhlv.hlv_gather_f32(ptrs, numel, 1, 128, 5, 1.0, 0, None, None, None, 0, None) == -1  # sum(numel) != dst_len
+
+
+def test_product_has_no_cpu_path():
+    import hessian_llm_vision_b200 as hlv
+    from hessian_llm_vision_b200 import kernels
+    v0 = torch.ones(16) / 4.0
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        hlv.lanczos(lambda v: v, 4, v0)
+    with pytest.raises(TypeError, match="CUDA"):
+        kernels.gather([torch.zeros(4)], torch.zeros(4))
+    # and nothing under the product package imports the oracle
+    pkg = os.path.join(ROOT, "hessian-llm-vision_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("oracle-", ""), fn
+
+
+# ---------------------------------------------------------------- Ritz / results
+def test_tridiag_eigh_matches_dense_eigh():
+    from hessian_llm_vision_b200 import ritz
+    rng = np.random.default_rng(0)
+    for m in (1, 2, 5, 40, 100):
+        a, b = rng.standard_normal(m), np.abs(rng.standard_normal(m))
+        vals, Y = ritz.tridiag_eigh(a, b)
+        T = ritz.dense_T(a, b, dtype=torch.float64)
+        ref = torch.linalg.eigvalsh(T).numpy()
+        assert np.allclose(vals, ref, atol=1e-10)
+        assert np.allclose(Y.T @ T.numpy() @ Y, np.diag(vals), atol=1e-9)
+        ev, gam, _ = ritz.ritz_values(a, b)
+        assert ev.dtype == torch.float32 and abs(float(gam.sum()) - 1) < 1e-5
+        assert abs(float((ev.double() * gam.double()).sum()) - a[0]) < 1e-4 * max(1, np.abs(ref).max())
+
+
+def test_kat_d2_through_host_lapack():
+    from hessian_llm_vision_b200 import ritz
+    ev, gam, _ = ritz.ritz_values([-0.638791, -1.283734, -0.975696, -0.539108], [22.250154, 23.118534, 22.320854, 0.0])
+    assert np.allclose(ev.numpy(), [-37.649489, -14.281579, 12.811337, 35.682401], atol=5e-5)
+    assert np.allclose(gam.numpy(), [0.133463, 0.361779, 0.369820, 0.134938], atol=5e-5)
+
+
+def test_eigeninfo_layout_roundtrip(tmp_path):
+    from hessian_llm_vision_b200 import results
+    p = results.eigeninfo_path("runs/ckpts/model_trained.pt", 0.0001, 25, False)
+    assert p == "runs/ckpts/subsample=0.0001_iters=25_basis=False/model_trained.pt.ckpt"
+    assert results.eigeninfo_path("a/b.pt", 1e-4, 30, True, "_noise").startswith("a/subsample=0.0001_iters=30_basis=True_noise/")
+    d = {"eigvals": torch.linspace(-1, 3, 25), "gammas": torch.full((25,), 1 / 25)}
+    out = str(tmp_path / "x" / "results.ckpt")
+    results.save_eigeninfo(d, out)
+    back = results.load_eigeninfo(out)
+    assert sorted(back) == ["eigvals", "gammas"] and back["eigvals"].dtype == torch.float32
+    assert torch.equal(back["eigvals"], d["eigvals"])
+    fn = results.save_tridiagonal_checkpoint(torch.eye(3), 997, 998, str(tmp_path / "70mpythia"))
+    assert fn.endswith("diego_data_seed=997_vector_seed=998/ckpt.pt")
+
+
+def test_slq_density_integrates_to_one():
+    from hessian_llm_vision_b200 import ritz
+    ev = [torch.tensor([-1.0, 0.0, 2.0]), torch.tensor([-0.5, 0.1, 2.5])]
+    gm = [torch.tensor([0.2, 0.5, 0.3]), torch.tensor([0.1, 0.6, 0.3])]
+    grid, dens = ritz.slq_density(ev, gm, sigma=0.05, margin=0.5, num_points=4000)
+    assert abs(np.trapezoid(dens, grid) - 1.0) < 1e-3
+
+
+# ---------------------------------------------------------------- engine host logic (test double)
+def _sym(seed, n):
+    torch.manual_seed(seed)
+    M = torch.randn(n, n)
+    M = (M + M.t()) / 2
+    v = torch.randn(n)
+    return M, v / v.norm()
+
+
+@pytest.mark.parametrize("reorth", [None, "full"])
+@pytest.mark.parametrize("n", [96, 101])
+def test_engine_control_flow_single_process(reorth, n):
+    import hessian_llm_vision_b200 as hlv
+    M, v0 = _sym(3, n)
+    m = 12
+    res = hlv.lanczos(lambda v: M @ v, m, v0, reorth=reorth, ops=fake_ops, keep_basis=True)
+    ref = oracle.lanczos_cgs2(lambda v: M @ v, v0, m, reorth=reorth)
+    scale = float(ref["T"].abs().max())
+    assert float((res.T - ref["T"]).abs().max()) / scale < 2e-5
+    assert res.m == m and not res.breakdown
+    assert float((res.Q - ref["Q"]).abs().max()) < 2e-4
+    V = res.ritz_vectors([m - 1])
+    assert V.shape == (1, n)
+    # pieces protocol: list return goes through gather (+ fused alpha)
+    sizes = [n // 3, n - n // 3]
+    res2 = hlv.lanczos(lambda v: list(torch.split(M @ v, sizes)), m, v0, reorth=reorth, ops=fake_ops)
+    assert float((res2.T - res.T).abs().max()) / scale < 1e-6
+
+
+def test_engine_breakdown_truncates():
+    import hessian_llm_vision_b200 as hlv
+    torch.manual_seed(1)
+    U, _ = torch.linalg.qr(torch.randn(64, 3))
+    H = (U * torch.tensor([3.0, 2.0, 1.0])) @ U.t()
+    v0 = U @ torch.tensor([0.5, 0.5, 0.70710678])
+    v0 /= v0.norm()
+    res = hlv.lanczos(lambda v: H @ v, 10, v0, reorth="full", ops=fake_ops, breakdown_tol=1e-5, check_every=1)
+    assert res.breakdown and res.m == 3
+    assert np.allclose(res.eigvals.numpy(), [1, 2, 3], atol=1e-4)
+
+
+def test_lanczos_tridiag_shim_shapes():
+    import hessian_llm_vision_b200 as hlv
+    M, v0 = _sym(5, 64)
+    calls = []
+
+    def closure(v):
+        calls.append(tuple(v.shape))
+        return M @ v
+    Q, T = hlv.lanczos_tridiag(closure, max_iter=6, dtype=torch.float32, device="cpu", matrix_shape=(64, 64),
+                               init_vecs=v0.unsqueeze(1), ops=fake_ops)
+    assert Q.shape == (64, 6) and T.shape == (6, 6)
+    assert all(s == (64, 1) for s in calls)                     # closure sees [P,1] like gpytorch's
+    assert float((Q.t() @ Q - torch.eye(6)).abs().max()) < 1e-5
+    assert float((Q.t() @ M @ Q - T).abs().max()) < 1e-3
+
+
+# ---------------------------------------------------------------- 2-rank gloo: sharded basis + batch-sharded HVP
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["HLV_ROOT"])
+import hessian_llm_vision_b200 as hlv
+from tests import fake_ops
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["HLV_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+n, m = int(os.environ["HLV_N"]), 14
+torch.manual_seed(3)
+# H = mean of `world` per-shard symmetric matrices: rank r applies only its own (batch-sharded HVP)
+Ms = []
+for r in range(world):
+    A = torch.randn(n, n); Ms.append((A + A.t()) / 2)
+v = torch.randn(n); v0 = v / v.norm()
+mine = Ms[rank] / world
+res = hlv.lanczos(lambda x: mine @ x, m, v0, reorth=os.environ["HLV_REORTH"] or None, ops=fake_ops,
+                  comm=hlv.Comm(), keep_basis=True)
+if rank == 0:
+    torch.save({"T": res.T, "n_local": res.n_local, "m": res.m}, os.environ["HLV_OUT"])
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("reorth,n", [("full", 100), ("", 64)])
+def test_sharded_engine_two_ranks_gloo(tmp_path, reorth, n):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    out = tmp_path / "res.pt"
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", HLV_ROOT=ROOT, HLV_PORT=str(port), HLV_N=str(n),
+                   HLV_REORTH=reorth, HLV_OUT=str(out), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        o, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, o.decode()[-2000:]
+    got = torch.load(out)
+    # single-process oracle of the SAME global operator
+    torch.manual_seed(3)
+    Ms = []
+    for r in range(2):
+        A = torch.randn(n, n); Ms.append((A + A.t()) / 2)
+    v = torch.randn(n); v0 = v / v.norm()
+    H = (Ms[0] + Ms[1]) / 2
+    ref = oracle.lanczos_cgs2(lambda x: H @ x, v0, 14, reorth=reorth or None)
+    scale = float(ref["T"].abs().max())
+    assert got["m"] == 14
+    assert got["n_local"] == ((n + 1) // 2 + 7) // 8 * 8
+    assert float((got["T"] - ref["T"]).abs().max()) / scale < (2e-5 if reorth else 2e-3)

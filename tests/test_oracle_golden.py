@@ -1,0 +1,251 @@
+"""Pin the CPU oracle: against the reference's own known-answer test, and against golden
+vectors produced by executing the reference's source (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+torch.set_num_threads(1)
+
+
+def _sym(seed, n):
+    torch.manual_seed(seed)
+    M = torch.randn(n, n)
+    M = (M + M.t()) / 2
+    v = torch.randn(n)
+    return M, v
+
+
+def _seed42():
+    # Discrepancy.ipynb cell 0: M += M.T.clone(); M = M/2
+    torch.manual_seed(42)
+    M = torch.randn([1000, 1000])
+    M += M.T.clone()
+    M = M / 2
+    v = torch.randn([1000, ])
+    return M, v
+
+
+def test_reference_kat_discrepancy_notebook():
+    """Discrepancy.ipynb cell 3 printed output: T and its eigenvalues (4 decimals)."""
+    M, v = _seed42()
+    T, _ = oracle.reorth_lanczos_mgs(lambda q: M @ q, v, 2)
+    assert np.allclose(T.numpy(), [[-0.6388, 22.2502], [22.2502, -1.2837]], atol=5e-5)
+    ev = torch.linalg.eigvalsh(T)
+    assert np.allclose(ev.numpy(), [-23.2138, 21.2912], atol=5e-5)
+
+
+def test_kat_d2_hand_loop_and_reorth_agree():
+    """SURVEY Appendix D.2 (derived, same seed): hand loop k=3 and reorth m=4."""
+    M, v = _seed42()
+    v0 = v / torch.norm(v, 2)
+    T_hand, Q = oracle.hand_lanczos(lambda q: M @ q, v0, 3)
+    T_re, _ = oracle.reorth_lanczos_mgs(lambda q: M @ q, v, 4)
+    diag = [-0.638791, -1.283734, -0.975696, -0.539108]
+    off = [22.250154, 23.118534, 22.320854]
+    for T in (T_hand, T_re):
+        assert np.allclose(np.diag(T.numpy()), diag, atol=2e-5)
+        assert np.allclose(np.diag(T.numpy(), 1), off, atol=2e-5)
+    ev, gam, _ = oracle.ritz(T_hand.double())
+    assert np.allclose(ev.numpy(), [-37.649489, -14.281579, 12.811337, 35.682401], atol=5e-5)
+    assert np.allclose(gam.numpy(), [0.133463, 0.361779, 0.369820, 0.134938], atol=5e-5)
+
+
+def test_golden_discrepancy_reorth_loop(golden_dir):
+    """G1: the notebook's own loop source, executed verbatim, m in {2,4,8,16}."""
+    g = np.load(os.path.join(golden_dir, "discrepancy_reorth.npz"))
+    M, v = _seed42()
+    for m in (2, 4, 8, 16):
+        T, basis = oracle.reorth_lanczos_mgs(lambda q: M @ q, v, m)
+        assert np.array_equal(T.numpy(), g[f"T_m{m}"]), f"m={m}"          # same ops, same order: bit-exact
+        assert np.array_equal(torch.stack(basis)[:, :8].numpy(), g[f"Q_m{m}_head"])
+
+
+def test_golden_hand_loop(golden_dir):
+    """G2: lanczostrain_hand.py:171-203 executed verbatim on dense symmetric matrices."""
+    g = np.load(os.path.join(golden_dir, "hand_lanczos.npz"))
+    for seed, n, k in ((42, 1000, 3), (7, 512, 10), (3, 2048, 24)):
+        M, v = _sym(seed, n)
+        if seed == 42:
+            pass
+        v0 = v / torch.norm(v, 2)
+        T, Q = oracle.hand_lanczos(lambda q: M @ q, v0, k)
+        assert np.array_equal(T.numpy(), g[f"T_s{seed}_n{n}_k{k}"])
+        assert np.array_equal(Q[:, :8].numpy(), g[f"Qhead_s{seed}_n{n}_k{k}"])
+
+
+def test_product_algorithm_reduces_to_hand_loop():
+    """lanczos_cgs2(reorth=None, m=k+1) is the hand loop, bit for bit."""
+    M, v = _sym(11, 300)
+    v0 = v / torch.norm(v, 2)
+    T, Q = oracle.hand_lanczos(lambda q: M @ q, v0, 9)
+    r = oracle.lanczos_cgs2(lambda q: M @ q, v0, 10, reorth=None)
+    assert torch.equal(r["T"], T)
+    assert torch.equal(r["Q"], Q)
+
+
+def test_cgs2_matches_reference_reorth_variant():
+    """The reference's MGS-reorth recurrence (A.3) and hand-loop-order + CGS2 are the same
+    Krylov process: T agrees to fp32 rounding while both are orthogonal."""
+    M, v = _seed42()
+    v0 = v / torch.norm(v, 2)
+    m = 30
+    T_ref, basis = oracle.reorth_lanczos_mgs(lambda q: M @ q, v, m)
+    r = oracle.lanczos_cgs2(lambda q: M @ q, v0, m, reorth="full")
+    scale = float(T_ref.abs().max())
+    assert float((r["T"] - T_ref).abs().max()) / scale < 1e-5
+    Q = r["Q"]
+    assert float((Q @ Q.t() - torch.eye(m)).abs().max()) < 5e-6
+    ev_ref = torch.linalg.eigvalsh(T_ref.double())
+    ev = torch.linalg.eigvalsh(r["T"].double())
+    assert float((ev - ev_ref).abs().max()) / scale < 1e-5
+
+
+def test_slq_properties():
+    M, v = _sym(5, 400)
+    v0 = v / torch.norm(v, 2)
+    r = oracle.lanczos_cgs2(lambda q: M @ q, v0, 40, reorth="full")
+    ev, gam, V = oracle.ritz(r["T"], r["Q"])
+    assert abs(float(gam.sum()) - 1.0) < 1e-5                     # sum gamma = 1
+    assert abs(float((ev * gam).sum()) - float(r["T"][0, 0])) < 1e-4   # sum gamma*lambda = alpha_0 = v0^T H v0
+    # Ritz vectors: rows orthonormal, Rayleigh quotients = Ritz values
+    assert float((V @ V.t() - torch.eye(40)).abs().max()) < 1e-4
+    rq = torch.einsum("ij,ij->i", V @ M, V)
+    assert float((rq - ev).abs().max()) / float(ev.abs().max()) < 1e-4
+
+
+def test_planted_spectrum_converges():
+    """Hessian-like spectrum with planted outliers: top Ritz values converge."""
+    torch.manual_seed(0)
+    n = 600
+    lam = torch.cat([torch.tensor([265.0, 44.0, 13.7]), 1.5 * torch.randn(n - 3)])
+    Qm, _ = torch.linalg.qr(torch.randn(n, n, dtype=torch.float64))
+    H = (Qm * lam.double()) @ Qm.t()
+    v = torch.randn(n)
+    v0 = v / v.norm()
+    r = oracle.lanczos_cgs2(lambda q: (H @ q.double()).float(), v0, 60, reorth="full")
+    ev = torch.linalg.eigvalsh(r["T"].double())
+    assert abs(float(ev[-1]) - 265.0) / 265.0 < 1e-5
+    assert abs(float(ev[-2]) - 44.0) / 44.0 < 1e-4
+    assert abs(float(ev[-3]) - 13.7) / 13.7 < 1e-3
+
+
+def test_bf16_basis_model():
+    M, v = _sym(9, 500)
+    v0 = v / torch.norm(v, 2)
+    r32 = oracle.lanczos_cgs2(lambda q: M @ q, v0, 20, reorth="full")
+    r16 = oracle.lanczos_cgs2(lambda q: M @ q, v0, 20, reorth="full", basis_dtype=torch.bfloat16)
+    assert torch.equal(r16["Q"], oracle.bf16_round(r16["Q"]))      # stored rows are bf16-representable
+    scale = float(r32["T"].abs().max())
+    assert float((r16["T"] - r32["T"]).abs().max()) / scale < 2e-2  # bf16 storage: ~1e-3-level agreement
+
+
+def test_breakdown_guard():
+    # rank-3 operator: Krylov space exhausted after 3 steps
+    torch.manual_seed(1)
+    U, _ = torch.linalg.qr(torch.randn(50, 3))
+    H = (U * torch.tensor([3.0, 2.0, 1.0])) @ U.t()
+    v0 = U @ torch.tensor([0.5, 0.5, 0.70710678])
+    v0 /= v0.norm()
+    r = oracle.lanczos_cgs2(lambda q: H @ q, v0, 10, reorth="full", breakdown_tol=1e-5)
+    assert r["m_eff"] == 3
+    ev = torch.linalg.eigvalsh(r["T"].double())
+    assert np.allclose(ev.numpy(), [1.0, 2.0, 3.0], atol=1e-4)
+
+
+# ---------------------------------------------------------------- HVP goldens
+def _tiny_model_from_golden(g):
+    from transformers import GPT2Config, GPT2LMHeadModel
+    cfg = GPT2Config(vocab_size=97, n_positions=16, n_embd=16, n_layer=2, n_head=2,
+                     attn_implementation="eager", resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    model = GPT2LMHeadModel(cfg)
+    sd = {k[len("state."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state.")}
+    model.load_state_dict(sd)
+    return model.eval()
+
+
+def test_golden_hvp_single_batch(golden_dir):
+    """G3: hess_vec of gpt2_hessian_cpu.py:75-109 executed on a tiny GPT-2."""
+    g = np.load(os.path.join(golden_dir, "tiny_gpt2_hvp.npz"))
+    model = _tiny_model_from_golden(g)
+    hv = oracle.hess_vec(torch.from_numpy(g["vec"]), torch.from_numpy(g["ids"]), model)
+    ref = torch.from_numpy(g["hv"])
+    assert float((hv - ref).abs().max()) <= 1e-6 * float(ref.abs().max()) + 1e-9
+
+
+def test_golden_hvp_dataset(golden_dir):
+    """G4: dataset hess_vec of gpt2_savehessian.py:130-163; the reference weights every batch by
+    len(batch)/N with batch a 2-key dict (quirk Q6) -> compare with weights 2/N."""
+    g = np.load(os.path.join(golden_dir, "tiny_gpt2_hvp.npz"))
+    model = _tiny_model_from_golden(g)
+    batches = [torch.from_numpy(g["ids"]), torch.from_numpy(g["ids2"])]
+    s = float(g["q6_scale"])
+    hv = oracle.hess_vec_dataset(torch.from_numpy(g["vec"]), batches, model, weights=[s, s])
+    ref = torch.from_numpy(g["hv_dataset_q6"])
+    assert float((hv - ref).abs().max()) <= 1e-6 * float(ref.abs().max()) + 1e-9
+
+
+def test_hvp_symmetry_and_variants(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tiny_gpt2_hvp.npz"))
+    model = _tiny_model_from_golden(g)
+    ids = torch.from_numpy(g["ids"])
+    P = g["vec"].shape[0]
+    torch.manual_seed(3)
+    a, b = torch.randn(P), torch.randn(P)
+    Ha, Hb = oracle.hess_vec(a, ids, model), oracle.hess_vec(b, ids, model)
+    assert abs(float(b @ Ha) - float(a @ Hb)) < 1e-4 * (abs(float(b @ Ha)) + 1e-3)   # H symmetric
+    # per-block operator = the block's rows/cols of the full Hessian
+    blk = list(model.transformer.h[1].parameters())
+    offs, off = {}, 0
+    for p in model.parameters():
+        offs[id(p)] = off
+        off += p.numel()
+    n_blk = sum(p.numel() for p in blk)
+    vb = torch.randn(n_blk)
+    full = torch.zeros(P)
+    o = 0
+    for p in blk:
+        full[offs[id(p)]: offs[id(p)] + p.numel()] = vb[o: o + p.numel()]
+        o += p.numel()
+    H_full = oracle.hess_vec(full, ids, model)
+    H_blk = oracle.hess_vec_subset(vb, [ids], model, blk)
+    o = 0
+    for p in blk:
+        seg = H_full[offs[id(p)]: offs[id(p)] + p.numel()]
+        assert float((seg - H_blk[o: o + p.numel()]).abs().max()) < 1e-5 * float(H_full.abs().max()) + 1e-8
+        o += p.numel()
+    # per-tensor operator: block-diagonal part only
+    Hpt = oracle.hess_vec_per_tensor(a, ids, model)
+    assert Hpt.shape == (P,)
+    assert float((Hpt - Ha).abs().max()) > 0      # differs from the full HVP (off-diagonal blocks dropped)
+
+
+def test_shipped_result_dict_layout(golden_dir):
+    """G5: the reference's shipped result dicts: keys, dtype, ascending, sum(gamma)=1."""
+    g = np.load(os.path.join(golden_dir, "shipped_result_dicts.npz"))
+    for tag, m in (("m25", 25), ("m35", 35), ("m30", 30)):
+        assert list(g[f"{tag}_keys"]) == ["eigvals", "gammas"]
+        ev, gam = g[f"{tag}_eigvals"], g[f"{tag}_gammas"]
+        assert ev.dtype == np.float32 and gam.dtype == np.float32 and ev.shape == (m,) == gam.shape
+        assert np.all(np.diff(ev) >= 0)
+        assert abs(float(gam.sum()) - 1.0) < 1e-5
+
+
+def test_lowrank_adjust_against_real_reference_kernel():
+    """oracle.lowrank_adjust vs the reference's vector_adjust.cu compiled for the host
+    (oracle/Makefile -> oracle/_ref/libvector_adjust_ref.so)."""
+    from oracle import ref_native
+    if not ref_native.have_cpu_ref():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(0)
+    for k, n in ((1, 33), (5, 700), (10, 1500)):
+        V = rng.standard_normal((k, n)).astype(np.float32)
+        gvec = rng.standard_normal(n).astype(np.float32)
+        eig = (rng.standard_normal(k) * 5).astype(np.float32)
+        adj = gvec.copy()
+        ref_native.vector_adjust_cpu(gvec, V, eig, adj, 1e-2)
+        o = oracle.lowrank_adjust(torch.from_numpy(gvec), torch.from_numpy(V), torch.from_numpy(eig), 1e-2).numpy()
+        assert np.abs(adj - o).max() <= 1e-5 * np.abs(o).max()
