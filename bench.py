@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Benchmark: Lanczos iterations/s for GPT-2 124M, m=100, full CGS2 reorthogonalisation, fp32 basis.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [...]                          # the reference's CPU path (gpt2_hessian_cpu.py shape)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is ONE Lanczos iteration (lanczostrain_hand.py:188-203 order): one Hessian-vector
+product of the GPT-2 loss over the global token batch by torch double-backward, the fused
+gather + alpha, the three-term update, two passes of classical Gram-Schmidt against every stored
+basis row, normalise + store.  The m=100 run has basis depth j = 0..99; with --steps 100 (default)
+the timed region IS that run; with another K, step i runs at depth floor((i+0.5)*100/K) over a
+pre-built orthonormal basis so the mean depth (hence mean cost) is that of the m=100 run.
+
+Scaling is STRONG: the global batch (64 sequences x 512 tokens = 8 per GPU at 8 GPUs, micro-batch
+8 = the reference's batch size) and therefore the operator and T are the same at every N; ranks
+shard the micro-batches (reduce-scatter of Hv) and the basis along the parameter dimension
+(k-float all-reduces).  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+M_DEPTH = 100
+SEQ_LEN = 512
+VOCAB = 50257
+METRIC = "lanczos_iters_per_sec_gpt2_124m_m100_cgs2"
+
+
+# --------------------------------------------------------------------------- helpers
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--global-batch", type=int, default=64)
+    ap.add_argument("--micro-batch", type=int, default=8)
+    ap.add_argument("--basis-dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cache-graph", action="store_true", help="keep the first-backward graph across iterations (extra, not the headline)")
+    ap.add_argument("--small", action="store_true", help="tiny model for a functional check of this script (NOT a benchmark)")
+    return ap.parse_args()
+
+
+def depth_schedule(K: int):
+    return [min(M_DEPTH - 1, int((i + 0.5) * M_DEPTH / K)) for i in range(K)]
+
+
+def build_model(small: bool):
+    from transformers import GPT2Config, GPT2LMHeadModel
+    if small:
+        cfg = GPT2Config(vocab_size=1024, n_positions=64, n_embd=64, n_layer=2, n_head=2, attn_implementation="eager",
+                         resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    else:   # the reference's model: GPT2Config(vocab_size=len(tokenizer), n_positions=512)  gpt2_hessian_cpu.py:142-143
+        cfg = GPT2Config(vocab_size=VOCAB, n_positions=SEQ_LEN, attn_implementation="eager")
+    torch.manual_seed(0)
+    return GPT2LMHeadModel(cfg).eval(), cfg
+
+
+def make_tokens(cfg, global_batch: int, micro_batch: int, seq_len: int):
+    g = torch.Generator().manual_seed(1234)            # precedent: gpt2_savehessian_noise.py:42-46
+    ids = torch.randint(0, cfg.vocab_size, (global_batch, seq_len), generator=g)
+    return [ids[i: i + micro_batch].contiguous() for i in range(0, global_batch, micro_batch)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel: str):
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------- reference's CPU path (oracle port)
+def reference_iteration_sampler(model_dev, batches_dev, weights, n, dev, host_rows: int):
+    """The faithful gpt2_hessian_cpu.py shape: HVP on the GPU by the reference's own
+    formulation (sum(v*g).backward(), torch.cat), `.cpu()` of the result every iteration
+    (gpt2_hessian_cpu.py:137), recurrence + full reorthogonalisation on HOST cores with torch CPU ops.
+    Returns step(depth) -> (t_non_cgs_s, t_cgs_s, rows_used)."""
+    import oracle   # CPU baseline leg only (the checker, timed as the baseline -- never the product path)
+    torch.manual_seed(99)
+    Qh = torch.zeros(host_rows, n)
+    for r in range(host_rows):           # synthetic orthonormal-ish host basis (values do not affect timing)
+        Qh[r].normal_()
+        Qh[r] /= Qh[r].norm()
+    state = {"v": Qh[0].clone(), "v_old": Qh[min(1, host_rows - 1)].clone()}
+
+    def step(depth_rows: int):
+        t0 = time.perf_counter()
+        v = state["v"]
+        w = oracle.hess_vec_dataset(v.to(dev), batches_dev, model_dev, weights=weights)   # H2D of v + GPU HVP
+        w = w.cpu()                                                                       # D2H, :137
+        alpha = torch.dot(w, v)                                                           # lanczostrain_hand.py:200
+        w -= (alpha * v + 0.5 * state["v_old"])                                           # :202
+        t1 = time.perf_counter()
+        rows = min(depth_rows, host_rows)
+        for _ in range(2):                                                                # CGS2 on host cores
+            c = Qh[:rows] @ w
+            w -= Qh[:rows].t() @ c
+        t2 = time.perf_counter()
+        b = torch.norm(w, 2)                                                              # :190-193
+        state["v_old"], state["v"] = v, w / b
+        t3 = time.perf_counter()
+        return (t1 - t0) + (t3 - t2), (t2 - t1), rows
+    return step
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    dev = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model, cfg = build_model(args.small)
+    model.to(dev)
+    seq = 64 if args.small else SEQ_LEN
+    batches = [b.to(dev) for b in make_tokens(cfg, args.global_batch, args.micro_batch, seq)]
+    weights = [b.shape[0] / args.global_batch for b in batches]
+    n = sum(p.numel() for p in model.parameters())
+    host_rows = 8
+    step = reference_iteration_sampler(model, batches, weights, n, dev, host_rows)
+    sched = depth_schedule(args.steps)
+    for i in range(args.warmup):
+        step(sched[i % len(sched)] + 1)
+    clocks = ClockSampler(0); clocks.start()
+    t_wall0 = time.perf_counter()
+    est = 0.0
+    for j in sched:
+        t_fix, t_cgs, rows = step(j + 1)
+        est += t_fix + t_cgs * (j + 1) / rows          # CGS cost is linear in the number of rows
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t_wall0
+    value = args.steps / est
+    cores = torch.get_num_threads()
+    sample = (f"{args.steps} iterations: real GPU HVP ({args.global_batch}x{seq} tokens) + .cpu() + host three-term update each; "
+              f"host CGS2 timed on {host_rows} resident rows and scaled linearly to the scheduled depth "
+              f"(mean depth {sum(sched) / len(sched) + 1:.1f} rows); wall {wall:.1f}s, scaled {est:.1f}s")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * est / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": bench_config(args, seq, n),
+            "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "clocks": clocks.stop(), "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(args, seq, n):
+    return {"workload": "GPT-2 124M (GPT2Config(vocab_size=50257, n_positions=512), random init seed 0, eager attention, fp32, TF32 off) "
+                        "Lanczos m=100 with full two-pass classical Gram-Schmidt reorthogonalisation, "
+                        f"{'fp32' if args.basis_dtype == 'f32' else 'bf16'} basis" if not args.small else "SMALL functional check (not a benchmark)",
+            "P": n, "global_batch": args.global_batch, "micro_batch": args.micro_batch, "seq_len": seq, "basis_depth": M_DEPTH,
+            "depth_schedule": "j=0..99 (the m=100 run itself)" if args.steps == M_DEPTH else f"floor((i+0.5)*100/{args.steps}) over a pre-built orthonormal basis",
+            "l2": "no flush: every pass streams >= 0.5 GB per basis row, far beyond the 126 MB L2",
+            "parallelism": f"{args.gpus} rank(s): micro-batches sharded (reduce-scatter of Hv), basis sharded along P (k-float all-reduce)"}
+
+
+# --------------------------------------------------------------------------- this repo's arm
+def run_ours(args, rank, world, local_rank):
+    import hessian_llm_vision_b200 as hlv
+    from hessian_llm_vision_b200 import kernels
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    comm = hlv.Comm()
+    model, cfg = build_model(args.small)
+    model.to(dev)
+    seq = 64 if args.small else SEQ_LEN
+    n = sum(p.numel() for p in model.parameters())
+    n_micro = args.global_batch // args.micro_batch
+    assert n_micro >= world and args.global_batch % args.micro_batch == 0, "need at least one micro-batch per rank"
+    all_batches = make_tokens(cfg, args.global_batch, args.micro_batch, seq)
+    mine_host = [b.pin_memory() for b in hlv.shard_batches(all_batches, rank, world)]
+    mine_dev = [b.to(dev) for b in mine_host]
+    op_dev = hlv.HessianVectorProduct(model, mine_dev, total_sequences=args.global_batch, cache_graph=args.cache_graph)
+    op_host = hlv.HessianVectorProduct(model, mine_host, total_sequences=args.global_batch, device=dev)
+    basis_dtype = torch.float32 if args.basis_dtype == "f32" else torch.bfloat16
+    eng = hlv.LanczosEngine(op_dev, n, M_DEPTH, dev, reorth="full", basis_dtype=basis_dtype, comm=comm, profile=True)
+    torch.manual_seed(7)                                  # probe: randn(P)/norm, diego_pythia.py:147-149
+    v0 = torch.randn(n)
+    v0 = (v0 / v0.norm()).to(dev)
+    sched = depth_schedule(args.steps)
+    real_run = args.steps == M_DEPTH
+
+    def prefill():
+        """Untimed setup: an orthonormal basis of depth 100 from a recurrence-only Lanczos run on a
+        synthetic diagonal operator (same kernels, no HVP)."""
+        g = torch.Generator(device=dev).manual_seed(11)
+        diag = torch.randn(n, device=dev, generator=g) / world     # every rank contributes diag*v/world; the sum is diag*v
+        keep, eng.hvp = eng.hvp, (lambda v: diag * v)
+        eng.start(v0)
+        for j in range(M_DEPTH):
+            eng.step(j)
+        eng.hvp = keep
+
+    def timed(op, e2e: bool):
+        eng.hvp = op
+        if real_run:
+            eng.start(v0)
+        eng.phases.pairs.clear()
+        comm.barrier(); torch.cuda.synchronize()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        launches0 = kernels.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        sink = 0.0
+        for j in sched:
+            eng.step(j)
+            if e2e:                                       # device -> host read of the step's result (alpha_j, beta_{j+1})
+                sink += float(eng.alphas[j].item()) + float(eng.betas[j + 1].item())
+        ev1.record()
+        torch.cuda.synchronize(); comm.barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item()), kernels.launch_count - launches0, (clocks.stop() if rank == 0 else None), eng.phases.summary()
+
+    prefill()
+    eng.hvp = op_dev
+    for i in range(max(args.warmup, 0)):
+        eng.step(sched[i % len(sched)])
+    torch.cuda.synchronize()
+
+    ms, launches, clocks, phases = timed(op_dev, e2e=False)
+    value = args.steps / (ms / 1e3)
+    ritz_top = None
+    if real_run:
+        res = eng.result()
+        ritz_top = [float(x) for x in res.eigvals[-3:]]
+
+    e2e = None
+    if not args.no_e2e:
+        h2d0 = op_host.h2d_bytes
+        ms_e, _, _, _ = timed(op_host, e2e=True)
+        e2e = {"value": args.steps / (ms_e / 1e3), "unit": "iterations/s",
+               "h2d_bytes_per_step": (op_host.h2d_bytes - h2d0) // args.steps, "d2h_bytes_per_step": 16,
+               "ms_per_step": ms_e / args.steps,
+               "api": "LanczosEngine.step over HessianVectorProduct with pinned-host token batches; alpha/beta read back every step"}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant libhlv kernel, from CUDA events inside the timed region ----
+    peak, peak_src = measured_peak()
+    s = 4 if args.basis_dtype == "f32" else 2
+    n_loc = eng.shard_n if world > 1 else n
+    kern_bytes = {
+        "cgs_project": lambda d: (d["rows"] * s + 4 * d["calls"]) * n_loc,
+        "cgs_update": lambda d: (d["rows"] * s + 8 * d["calls"]) * n_loc,
+        "update": lambda d: 16 * n_loc * d["calls"],
+        "normalize": lambda d: (4 + s) * n_loc * d["calls"] if s == 4 else (4 + 4 + s) * n_loc * d["calls"],
+        "gather": lambda d: (8 + 4) * n * d["calls"],      # read pieces 4n + write w 4n (+4n v for the fused alpha on the last micro-batch)
+        "dot": lambda d: 8 * n_loc * d["calls"],
+    }
+    kernels_out = {}
+    for name, fn in kern_bytes.items():
+        if name in phases and phases[name]["ms"] > 0:
+            d = phases[name]
+            gbs = fn(d) / (d["ms"] * 1e-3) / 1e9
+            kernels_out[name] = {"ms_total": round(d["ms"], 3), "launches": d["calls"], "achieved_gbs": round(gbs, 1),
+                                 "frac_of_peak": round(gbs / peak, 4)}
+    ours_ms = sum(v["ms_total"] for v in kernels_out.values())
+    top = max((k for k in kernels_out if k.startswith("cgs")), key=lambda k: kernels_out[k]["ms_total"], default=None)
+    roofline = None
+    if top:
+        kname = f"hlv::{top}_kernel<{'float' if s == 4 else 'bf16'}>"
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": kernels_out[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels_out[top]["frac_of_peak"], "traffic": ncu_traffic(top), "peak_source": peak_src,
+                    "bytes_model": "project: (rows*s+4)*n per launch; update: (rows*s+8)*n per launch (DESIGN.md)",
+                    "share_of_step": round(kernels_out[top]["ms_total"] / ms, 4)}
+    line = {"metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": bench_config(args, seq, n),
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "kernels": kernels_out,
+            "recurrence_only": {"ms_per_step": ours_ms / args.steps, "iterations_per_s": args.steps / (ours_ms / 1e3) if ours_ms else None,
+                                "note": "sum of libhlv kernel time (CUDA events) in the timed region; HVP (torch) excluded"},
+            "hvp_ms_per_step": phases.get("hvp", {}).get("ms", 0.0) / args.steps,
+            "ritz_top3": ritz_top}
+    # ---- CPU baseline: the reference's CPU path on this box's host cores (rank 0, N=1 only) ----
+    if world == 1 and not args.no_cpu_baseline:
+        del eng
+        torch.cuda.empty_cache()
+        host_rows = 8
+        step = reference_iteration_sampler(model, mine_dev, op_dev.weights, n, dev, host_rows)
+        step(host_rows)                                   # warm
+        reps, t_fix, t_cgs = 3, 0.0, 0.0
+        for _ in range(reps):
+            a, b, rows = step(host_rows)
+            t_fix += a / reps; t_cgs += b / reps
+        mean_rows = sum(depth_schedule(M_DEPTH)) / M_DEPTH + 1
+        t_iter = t_fix + t_cgs * mean_rows / host_rows
+        line["cpu_baseline"] = {"value": 1.0 / t_iter, "unit": "iterations/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{reps} iterations of the gpt2_hessian_cpu.py shape (GPU HVP + .cpu() + host recurrence {t_fix:.2f}s; "
+                                          f"host CGS2 on {host_rows} rows {t_cgs:.2f}s scaled linearly to the m=100 mean depth {mean_rows:.1f} rows)",
+                                "os_cpu_count": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,254 @@
+"""-m gpu: every libhlv kernel, called through the C ABI, against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+GPT2_SHAPES = ([(50257, 768), (512, 768)] +
+               [s for _ in range(12) for s in [(768,), (768,), (768, 2304), (2304,), (768, 768), (768,), (768,), (768,),
+                                               (768, 3072), (3072,), (3072, 768), (768,)]] +
+               [(768,), (768,)])
+
+
+@pytest.fixture(scope="module")
+def K(cuda_dev, libhlv):
+    from hessian_llm_vision_b200 import kernels
+    return kernels
+
+
+def _ws(K, dev, rows=128):
+    return K.Workspace(dev, max_rows=rows)
+
+
+# ------------------------------------------------------------------ (a) gather / scatter
+def test_gather_scatter_gpt2_full_size_bit_exact(K, cuda_dev):
+    """The real thing: GPT-2's 148 tensors, P = 124,046,592, vs torch.cat, bit for bit."""
+    assert len(GPT2_SHAPES) == 148
+    g = torch.Generator(device=cuda_dev).manual_seed(0)
+    tensors = [torch.randn(*s, device=cuda_dev, generator=g) for s in GPT2_SHAPES]
+    P = sum(t.numel() for t in tensors)
+    assert P == 124_046_592
+    v = torch.randn(P, device=cuda_dev, generator=g)
+    dst = torch.empty(P, device=cuda_dev)
+    dot = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+    ws = _ws(K, cuda_dev)
+    K.gather(tensors, dst, dot_with=v, dot_out=dot, ws=ws)
+    ref = torch.cat([t.view(-1) for t in tensors])
+    assert torch.equal(dst, ref)
+    exact = torch.dot(ref.double(), v.double()).item()
+    assert abs(dot.item() - exact) <= 1e-6 * float(torch.linalg.vector_norm(ref.double()) * torch.linalg.vector_norm(v.double()))
+    # plain gather (no dot) and scatter back
+    dst2 = torch.zeros(P, device=cuda_dev)
+    K.gather(tensors, dst2)
+    assert torch.equal(dst2, ref)
+    outs = [torch.zeros_like(t) for t in tensors]
+    K.scatter(dst2, outs)
+    for a, b in zip(outs, tensors):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("sizes", [
+    [1], [3, 5, 7], [0, 4, 0, 9, 1], [1023, 1, 4097, 2, 8191, 8193], [64, 3, 9408, 64, 64, 1000, 10],
+    [17] * 300,                       # > 224 tensors: large parameter table
+    [5] * 1500,                       # > 1024 tensors: chunked launches
+])
+def test_gather_ragged_unaligned(K, cuda_dev, sizes):
+    """Odd sizes put every segment boundary off the 16-byte grid (ResNet-like); empty tensors; long lists."""
+    g = torch.Generator(device=cuda_dev).manual_seed(1)
+    tensors = [torch.randn(s, device=cuda_dev, generator=g) for s in sizes]
+    P = sum(sizes)
+    ref = torch.cat([t.view(-1) for t in tensors]) if P else torch.zeros(0, device=cuda_dev)
+    v = torch.randn(P, device=cuda_dev, generator=g)
+    dst = torch.full((P,), float("nan"), device=cuda_dev)
+    dot = torch.full((1,), float("nan"), dtype=torch.float64, device=cuda_dev)
+    ws = _ws(K, cuda_dev)
+    K.gather(tensors, dst, dot_with=v, dot_out=dot, ws=ws)
+    assert torch.equal(dst, ref)
+    assert abs(dot.item() - torch.dot(ref.double(), v.double()).item()) < 1e-4 * (1 + P ** 0.5)
+    outs = [torch.full_like(t, float("nan")) for t in tensors]
+    K.scatter(dst, outs)
+    for a, b in zip(outs, tensors):
+        assert torch.equal(a, b)
+
+
+def test_gather_views_with_offset_sources(K, cuda_dev):
+    """Sources that are 4-byte but not 16-byte aligned (views into a larger buffer)."""
+    big = torch.randn(10_000, device=cuda_dev)
+    tensors = [big[1:1001], big[2003:2010], big[3002:7003]]
+    dst = torch.empty(sum(t.numel() for t in tensors), device=cuda_dev)
+    K.gather([t.contiguous() if not t.is_contiguous() else t for t in tensors], dst)
+    assert torch.equal(dst, torch.cat(tensors))
+
+
+def test_gather_scale_accumulate(K, cuda_dev):
+    g = torch.Generator(device=cuda_dev).manual_seed(2)
+    sizes = [1000, 33, 4096, 7]
+    a = [torch.randn(s, device=cuda_dev, generator=g) for s in sizes]
+    b = [torch.randn(s, device=cuda_dev, generator=g) for s in sizes]
+    P = sum(sizes)
+    v = torch.randn(P, device=cuda_dev, generator=g)
+    dst = torch.empty(P, device=cuda_dev)
+    dot = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+    ws = _ws(K, cuda_dev)
+    K.gather(a, dst)
+    K.gather(b, dst, scale=0.25, accumulate=True, dot_with=v, dot_out=dot, ws=ws)
+    ref = torch.cat(a) + 0.25 * torch.cat(b)
+    assert torch.allclose(dst, ref, rtol=1e-6, atol=1e-7)
+    assert abs(dot.item() - torch.dot(dst.double(), v.double()).item()) < 1e-3
+
+
+# ------------------------------------------------------------------ (b) recurrence
+@pytest.mark.parametrize("n", [1, 7, 1024, 4099, 1_000_003, 8 * 1024 * 1024])
+def test_dot_update_normalize(K, cuda_dev, n):
+    g = torch.Generator(device=cuda_dev).manual_seed(n)
+    w = torch.randn(n, device=cuda_dev, generator=g)
+    vj = torch.randn(n, device=cuda_dev, generator=g)
+    vo = torch.randn(n, device=cuda_dev, generator=g)
+    ws = _ws(K, cuda_dev)
+    out = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+    K.dot(w, vj, out, ws)
+    exact = torch.dot(w.double(), vj.double()).item()
+    assert abs(out.item() - exact) <= 2e-6 * (n ** 0.5) * 3 + 1e-6
+    # three-term update: bit-identical to torch's elementwise sequence given the same scalars
+    alpha = torch.tensor([0.7310585], dtype=torch.float64, device=cuda_dev)
+    beta = torch.tensor([1.6180339], dtype=torch.float64, device=cuda_dev)
+    nrm = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+    w1 = w.clone()
+    K.lanczos_update(w1, vj, vo, alpha, beta, nrm, ws)
+    ref = w - (alpha.float() * vj + beta.float() * vo)          # lanczostrain_hand.py:202
+    assert torch.equal(w1, ref)
+    assert abs(nrm.item() - torch.dot(ref.double(), ref.double()).item()) <= 1e-6 * nrm.item() + 1e-9
+    w0 = w.clone()
+    K.lanczos_update(w0, vj, None, alpha, None, nrm, ws)
+    assert torch.equal(w0, w - alpha.float() * vj)               # :185
+    # normalise + store: beta = sqrt(norm2), v = w / beta with true division
+    K.lanczos_update(w1, vj, vo, torch.zeros_like(alpha), torch.zeros_like(beta), nrm, ws)   # nrm = |w1|^2
+    beta_out = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+    n8 = (n + 7) // 8 * 8
+    v_out = torch.zeros(n8, device=cuda_dev)[:n]
+    row16 = torch.zeros(n8, dtype=torch.bfloat16, device=cuda_dev)[:n]
+    flag = torch.full((1,), -1, dtype=torch.int32, device=cuda_dev)
+    K.normalize_store(w1, nrm, beta_out, v_out, row16, 0.0, flag, 3)
+    b32 = beta_out.float()
+    assert abs(beta_out.item() - torch.linalg.vector_norm(w1.double()).item()) <= 1e-6 * beta_out.item()
+    assert torch.equal(v_out, w1 / b32)                          # :193
+    assert torch.equal(row16, (w1 / b32).to(torch.bfloat16))
+    assert flag.item() == -1
+    K.normalize_store(w1, nrm, beta_out, None, None, 1e30, flag, 5)    # beta-only + breakdown flag
+    assert flag.item() == 5
+
+
+# ------------------------------------------------------------------ (c) CGS project / update
+def _basis(rows, n, dev, dtype, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    ld = (n + 7) // 8 * 8
+    V = torch.zeros(rows, ld, device=dev, dtype=dtype)
+    V[:, :n] = (torch.randn(rows, n, device=dev, generator=g) / n ** 0.5).to(dtype)
+    w = torch.randn(n, device=dev, generator=g)
+    return V, w
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,n", [(1, 1), (1, 2048), (3, 5), (8, 2048), (9, 4096), (13, 2049), (100, 65536 + 17),
+                                    (37, 1_000_003), (128, 300_000), (5, 23_528_522)])
+def test_cgs_project_update(K, cuda_dev, dtype, rows, n):
+    V, w = _basis(rows, n, cuda_dev, dtype, rows * 7 + n)
+    ws = _ws(K, cuda_dev, rows)
+    c = torch.full((rows,), float("nan"), dtype=torch.float64, device=cuda_dev)
+    K.cgs_project(V, rows, w, c, ws)
+    Vd = V[:, :n].double()
+    c_ref = Vd @ w.double()
+    tol = 3e-6 * float((Vd.abs() @ w.double().abs()).max()) + 1e-12
+    assert float((c - c_ref).abs().max()) <= tol
+    # update (sign=-1) + norm
+    w1 = w.clone()
+    nrm = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+    K.cgs_update(V, rows, c, w1, nrm, ws)
+    w_ref = w.double() - Vd.t() @ c.float().double()
+    assert float((w1.double() - w_ref).abs().max()) <= 1e-5 * float(w_ref.abs().max())
+    assert abs(nrm.item() - float(w_ref @ w_ref)) <= 1e-5 * nrm.item()
+    # determinism: same inputs -> same bits (fixed-order reductions)
+    c2 = torch.zeros_like(c)
+    K.cgs_project(V, rows, w, c2, ws)
+    assert torch.equal(c, c2)
+    # sign=+1 restores w
+    K.cgs_update(V, rows, c, w1, None, ws, sign=1.0)
+    assert float((w1 - w).abs().max()) <= 1e-5 * float(w.abs().max())
+
+
+def test_cgs2_orthogonalises_full_size(K, cuda_dev):
+    """BASELINE full size (n = GPT-2's P), size-independent properties: after CGS2 against an
+    orthonormal basis the result is orthogonal to every row, and the pass is idempotent."""
+    n, rows = 124_046_592, 12
+    g = torch.Generator(device=cuda_dev).manual_seed(0)
+    V = torch.zeros(rows, n, device=cuda_dev)
+    ws = _ws(K, cuda_dev, rows)
+    c = torch.zeros(rows, dtype=torch.float64, device=cuda_dev)
+    nrm = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+    beta = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+    for j in range(rows):                       # build an orthonormal basis with the kernels themselves
+        w = torch.randn(n, device=cuda_dev, generator=g)
+        if j:
+            for _ in range(2):
+                K.cgs_project(V, j, w, c, ws)
+                K.cgs_update(V, j, c, w, nrm, ws)
+        else:
+            K.dot(w, w, nrm, ws)
+        K.normalize_store(w, nrm, beta, V[j], None)
+    Vd = V.double()
+    G = Vd @ Vd.t()
+    del Vd
+    assert float((G - torch.eye(rows, dtype=torch.float64, device=cuda_dev)).abs().max()) < 1e-6
+    w = torch.randn(n, device=cuda_dev, generator=g)
+    for _ in range(2):
+        K.cgs_project(V, rows, w, c, ws)
+        K.cgs_update(V, rows, c, w, nrm, ws)
+    K.cgs_project(V, rows, w, c, ws)
+    assert float(c.abs().max()) < 1e-5 * nrm.item() ** 0.5       # orthogonal to every row
+    w2 = w.clone()
+    K.cgs_update(V, rows, c, w2, nrm, ws)
+    assert float((w2 - w).abs().max()) <= 1e-6 * float(w.abs().max())   # idempotent
+
+
+# ------------------------------------------------------------------ vector_adjust / Ritz vectors
+@pytest.mark.parametrize("k,n", [(1, 33), (5, 700), (10, 4096), (10, 100_003)])
+def test_vector_adjust_vs_oracle_and_reference_kernel(K, cuda_dev, k, n):
+    from hessian_llm_vision_b200 import adjust
+    from oracle import ref_native
+    g = torch.Generator(device=cuda_dev).manual_seed(k * n)
+    V = torch.randn(k, n, device=cuda_dev, generator=g) / n ** 0.5
+    if n % 4:
+        ld = (n + 7) // 8 * 8
+        Vp = torch.zeros(k, ld, device=cuda_dev)
+        Vp[:, :n] = V
+        Vk = Vp[:, :n]
+    else:
+        Vk = V
+    grad = torch.randn(n, device=cuda_dev, generator=g)
+    eig = (torch.randn(k, device=cuda_dev, generator=g) * 5).abs() + 0.1
+    delta = 1e-2
+    adj = grad.clone()
+    adjust.cuda_vector_adjust(grad, Vk, eig, adj, delta)
+    ref = oracle.lowrank_adjust(grad.cpu(), V.cpu(), eig.cpu(), delta)
+    assert float((adj.cpu() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    if n <= 4096 and ref_native.have_cubin():
+        # the reference's own kernel (O(k n^2)), compiled from /root/reference/vector_adjust.cu
+        adj_ref = grad.clone()
+        ref_native.vector_adjust_gpu(grad, V.contiguous(), eig, adj_ref, delta)
+        assert float((adj - adj_ref).abs().max()) <= 2e-5 * float(adj_ref.abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("m,nvec,n", [(4, 4, 100), (25, 3, 70_001), (100, 17, 200_000)])
+def test_ritz_vectors(K, cuda_dev, dtype, m, nvec, n):
+    Q, _ = _basis(m, n, cuda_dev, dtype, m + n)
+    g = torch.Generator(device=cuda_dev).manual_seed(5)
+    Y = torch.randn(m, nvec, device=cuda_dev, generator=g)
+    ld = (n + 7) // 8 * 8
+    out = torch.full((nvec, ld), float("nan"), device=cuda_dev)
+    K.ritz_vectors(Q, m, Y, out, n)
+    ref = Y.double().t() @ Q[:, :n].double()                     # eigvects.t() @ Q
+    assert float((out[:, :n].double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())

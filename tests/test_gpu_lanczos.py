@@ -1,0 +1,320 @@
+"""-m gpu: the Lanczos engine end to end through libhlv, against the CPU oracle, the
+reference's known-answer test and the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hlv(cuda_dev, libhlv):
+    import hessian_llm_vision_b200 as hlv
+    return hlv
+
+
+def _seed42():
+    torch.manual_seed(42)
+    M = torch.randn([1000, 1000])
+    M += M.T.clone()
+    M = M / 2
+    v = torch.randn([1000, ])
+    return M, v
+
+
+def _sym(seed, n):
+    torch.manual_seed(seed)
+    M = torch.randn(n, n)
+    M = (M + M.t()) / 2
+    v = torch.randn(n)
+    return M, v / v.norm()
+
+
+def _rel(a, b, scale):
+    return float((a.double().cpu() - b.double().cpu()).abs().max()) / scale
+
+
+def test_reference_kat_through_the_cuda_path(hlv, cuda_dev, golden_dir):
+    """Discrepancy.ipynb cell 3: T = [[-0.6388, 22.2502],[22.2502, -1.2837]], eig [-23.2138, 21.2912];
+    and the m=16 golden T produced by the notebook's own reorth loop."""
+    M, v = _seed42()
+    Md = M.to(cuda_dev)
+    v0 = (v / torch.norm(v, 2)).to(cuda_dev)
+    res = hlv.lanczos(lambda q: Md @ q, 2, v0, reorth="full")
+    assert np.allclose(res.T.numpy(), [[-0.6388, 22.2502], [22.2502, -1.2837]], atol=1e-4)
+    assert np.allclose(res.eigvals.numpy(), [-23.2138, 21.2912], atol=1e-4)
+    g = np.load(os.path.join(golden_dir, "discrepancy_reorth.npz"))
+    res16 = hlv.lanczos(lambda q: Md @ q, 16, v0, reorth="full")
+    T_ref = torch.from_numpy(g["T_m16"])
+    assert _rel(res16.T, T_ref, float(T_ref.abs().max())) < 1e-5        # alpha/beta within 1e-5 relative
+
+
+@pytest.mark.parametrize("seed,n,k", [(42, 1000, 3), (7, 512, 10), (3, 2048, 24)])
+def test_hand_loop_no_reorth_vs_golden(hlv, cuda_dev, golden_dir, seed, n, k):
+    """reorth=None is the reference hand loop (lanczostrain_hand.py:171-203); golden T from its source.
+    Without reorthogonalisation fp32 runs of the SAME loop drift apart, so the per-
+    iteration check covers the iterations whose basis is still orthogonal; the rest is checked
+    through the converged extreme Ritz values."""
+    g = np.load(os.path.join(golden_dir, "hand_lanczos.npz"))
+    T_ref = torch.from_numpy(g[f"T_s{seed}_n{n}_k{k}"])
+    M, v0 = _sym(seed, n)
+    Md = M.to(cuda_dev)
+    res = hlv.lanczos(lambda q: Md @ q, k + 1, v0.to(cuda_dev), reorth=None, keep_basis=True)
+    assert res.T.shape == T_ref.shape
+    scale = float(T_ref.abs().max())
+    head = min(k + 1, 8)
+    assert _rel(res.T[:head, :head], T_ref[:head, :head], scale) < 1e-5
+    assert _rel(res.T, T_ref, scale) < 5e-3
+    assert abs(float(res.eigvals[-1]) - float(torch.linalg.eigvalsh(T_ref.double())[-1])) / scale < 1e-3
+    Qh = torch.from_numpy(g[f"Qhead_s{seed}_n{n}_k{k}"])
+    assert float((res.Q[:head, :8].cpu() - Qh[:head]).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("n,m", [(1000, 30), (4096, 100), (100_003, 40)])
+def test_full_reorth_vs_oracle(hlv, cuda_dev, n, m):
+    """CGS2 run vs the oracle: alpha/beta within 1e-5 relative per iteration, Ritz within 1e-4."""
+    torch.manual_seed(n)
+    if n <= 4096:
+        M, v0 = _sym(n, n)
+        Md = M.to(cuda_dev)
+        op_gpu = lambda q: Md @ q
+        op_cpu = lambda q: M @ q
+    else:                               # structured operator: diagonal + rank-2, cheap at any n
+        d = torch.randn(n) * 1.5
+        d[:3] = torch.tensor([265.0, 44.0, 13.7])
+        u = torch.randn(n) / n ** 0.5
+        v = torch.randn(n)
+        v0 = v / v.norm()
+        dd, ud = d.to(cuda_dev), u.to(cuda_dev)
+        op_gpu = lambda q: dd * q + ud * torch.dot(ud, q)
+        op_cpu = lambda q: d * q + u * torch.dot(u, q)
+    res = hlv.lanczos(op_gpu, m, v0.to(cuda_dev), reorth="full")
+    ref = oracle.lanczos_cgs2(op_cpu, v0, m, reorth="full")
+    scale = float(ref["T"].abs().max())
+    assert _rel(res.alphas, ref["alphas"], scale) < 1e-5
+    assert _rel(res.betas, ref["betas"], scale) < 1e-5
+    ev_ref = torch.linalg.eigvalsh(ref["T"].double())
+    assert _rel(res.eigvals, ev_ref, scale) < 1e-4
+    top = slice(-5, None)
+    assert float(((res.eigvals.double()[top] - ev_ref[top]) / ev_ref[top]).abs().max()) < 1e-4   # top-k, relative
+    Q = res.Q.double()
+    assert float((Q @ Q.t() - torch.eye(m, dtype=torch.float64, device=cuda_dev)).abs().max()) < 5e-6
+    assert abs(float(res.gammas.sum()) - 1) < 1e-5
+    assert abs(float((res.eigvals * res.gammas).sum()) - float(res.alphas[0])) < 1e-4 * scale
+
+
+def test_bf16_basis_vs_bf16_oracle(hlv, cuda_dev):
+    M, v0 = _sym(9, 2000)
+    Md = M.to(cuda_dev)
+    m = 24
+    res = hlv.lanczos(lambda q: Md @ q, m, v0.to(cuda_dev), reorth="full", basis_dtype=torch.bfloat16)
+    ref = oracle.lanczos_cgs2(lambda q: M @ q, v0, m, reorth="full", basis_dtype=torch.bfloat16)
+    scale = float(ref["T"].abs().max())
+    assert res.basis.dtype == torch.bfloat16
+    assert _rel(res.T, ref["T"], scale) < 2e-3                  # bf16 rounding amplifies fp32 reduction-order noise
+    ref32 = oracle.lanczos_cgs2(lambda q: M @ q, v0, m, reorth="full")
+    assert _rel(res.eigvals[-3:], torch.linalg.eigvalsh(ref32["T"].double())[-3:], scale) < 1e-2
+    assert float((res.Q[:m].float().cpu() - ref["Q"]).abs().max()) < 5e-2
+
+
+def test_pieces_protocol_and_ritz_vectors(hlv, cuda_dev):
+    M, v0 = _sym(5, 1536)
+    Md = M.to(cuda_dev)
+    sizes = [768, 5, 763]
+    m = 20
+    res = hlv.lanczos(lambda q: [p.contiguous() for p in torch.split(Md @ q, sizes)], m, v0.to(cuda_dev), reorth="full")
+    ref = oracle.lanczos_cgs2(lambda q: M @ q, v0, m, reorth="full")
+    scale = float(ref["T"].abs().max())
+    assert _rel(res.T, ref["T"], scale) < 1e-5
+    ev, gam, V = oracle.ritz(ref["T"], ref["Q"])
+    which = [m - 1, m - 2, 0]
+    Vg = res.ritz_vectors(which).cpu()
+    for r, i in enumerate(which):                      # Ritz vectors are defined up to sign
+        a, b = Vg[r], V[i]
+        assert min(float((a - b).abs().max()), float((a + b).abs().max())) < 1e-3
+    d = res.eigeninfo(basis=True)
+    assert sorted(d) == ["V", "eigvals", "gammas"] and d["V"].shape == (m, 1536)
+
+
+def test_breakdown_on_device(hlv, cuda_dev):
+    torch.manual_seed(1)
+    U, _ = torch.linalg.qr(torch.randn(64, 3))
+    H = ((U * torch.tensor([3.0, 2.0, 1.0])) @ U.t()).to(cuda_dev)
+    v0 = U @ torch.tensor([0.5, 0.5, 0.70710678])
+    v0 /= v0.norm()
+    res = hlv.lanczos(lambda q: H @ q, 10, v0.to(cuda_dev), reorth="full", breakdown_tol=1e-5)
+    assert res.breakdown and res.m == 3
+    assert np.allclose(res.eigvals.numpy(), [1, 2, 3], atol=1e-4)
+
+
+def test_lanczos_tridiag_shim_on_gpu(hlv, cuda_dev):
+    M, v0 = _sym(5, 640)
+    Md = M.to(cuda_dev)
+    shapes = []
+
+    def closure(v):
+        shapes.append(tuple(v.shape))
+        return Md @ v
+    Q, T = hlv.lanczos_tridiag(closure, max_iter=10, dtype=torch.float32, device="cuda", matrix_shape=(640, 640),
+                               init_vecs=v0.to(cuda_dev).unsqueeze(1))
+    assert Q.shape == (640, 10) and T.shape == (10, 10) and Q.is_cuda
+    assert all(s == (640, 1) for s in shapes)
+    ref = oracle.lanczos_cgs2(lambda q: M @ q, v0, 10, reorth="full")
+    assert _rel(T, ref["T"], float(ref["T"].abs().max())) < 1e-5
+    # host-resident results, as gpt2_hessian_cpu.py:211 asks for
+    Qc, Tc = hlv.lanczos_tridiag(closure, max_iter=4, dtype=torch.float32, device="cpu", matrix_shape=(640, 640),
+                                 init_vecs=v0.to(cuda_dev).unsqueeze(1))
+    assert not Qc.is_cuda and not Tc.is_cuda
+
+
+# ---------------------------------------------------------------- HVP operators
+def _tiny_model(g):
+    from transformers import GPT2Config, GPT2LMHeadModel
+    cfg = GPT2Config(vocab_size=97, n_positions=16, n_embd=16, n_layer=2, n_head=2,
+                     attn_implementation="eager", resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    model = GPT2LMHeadModel(cfg)
+    sd = {k[len("state."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state.")}
+    model.load_state_dict(sd)
+    return model.eval()
+
+
+def test_hvp_operator_vs_reference_golden(hlv, cuda_dev, golden_dir):
+    """HessianVectorProduct (double-backward + libhlv gather) vs the golden Hv computed by the
+    reference's own hess_vec source (gpt2_hessian_cpu.py:75-109, gpt2_savehessian.py:130-163)."""
+    g = np.load(os.path.join(golden_dir, "tiny_gpt2_hvp.npz"))
+    model = _tiny_model(g).to(cuda_dev)
+    vec = torch.from_numpy(g["vec"]).to(cuda_dev)
+    ids, ids2 = torch.from_numpy(g["ids"]).to(cuda_dev), torch.from_numpy(g["ids2"]).to(cuda_dev)
+    hv_ref = torch.from_numpy(g["hv"])
+    op = hlv.HessianVectorProduct(model, [ids])
+    hv = op(vec)
+    assert _rel(hv, hv_ref, float(hv_ref.abs().max())) < 2e-5
+    assert op(vec.unsqueeze(1)).shape == (vec.numel(), 1)
+    for cache in (False, True):                            # cached first-backward graph: same operator
+        opc = hlv.HessianVectorProduct(model, [ids], cache_graph=cache)
+        assert _rel(opc(vec), hv_ref, float(hv_ref.abs().max())) < 2e-5
+        assert _rel(opc(vec), hv_ref, float(hv_ref.abs().max())) < 2e-5
+    s = float(g["q6_scale"])
+    op_ds = hlv.HessianVectorProduct(model, [ids, ids2], weights=[s, s])
+    ref_ds = torch.from_numpy(g["hv_dataset_q6"])
+    assert _rel(op_ds(vec), ref_ds, float(ref_ds.abs().max())) < 2e-5
+    # reference adapter class: [P,1] -> [P,1] on device
+    cvp = hlv.CurvVecProduct([ids], model, init_vec=vec)
+    assert _rel(cvp(vec.unsqueeze(1)).squeeze(1), hv_ref, float(hv_ref.abs().max())) < 2e-5
+
+
+def test_block_and_per_tensor_operators(hlv, cuda_dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "tiny_gpt2_hvp.npz"))
+    model_cpu = _tiny_model(g)
+    model = _tiny_model(g).to(cuda_dev)
+    ids = torch.from_numpy(g["ids"])
+    blk_cpu = list(model_cpu.transformer.h[1].parameters())
+    blk = list(model.transformer.h[1].parameters())
+    nb = sum(p.numel() for p in blk)
+    torch.manual_seed(4)
+    vb = torch.randn(nb)
+    ref = oracle.hess_vec_subset(vb, [ids], model_cpu, blk_cpu)            # visual-eigen.ipynb cell 10
+    got = hlv.HessianVectorProduct(model, [ids.to(cuda_dev)], params=blk)(vb.to(cuda_dev))
+    assert _rel(got, ref, float(ref.abs().max())) < 2e-5
+    vec = torch.from_numpy(g["vec"])
+    ref_pt = oracle.hess_vec_per_tensor(vec, ids, model_cpu)               # gpt2_savehessian_layer.py:155-173
+    got_pt = hlv.HessianVectorProduct(model, [ids.to(cuda_dev)], per_tensor=True)(vec.to(cuda_dev))
+    assert _rel(got_pt, ref_pt, float(ref_pt.abs().max())) < 2e-5
+
+
+def test_tiny_gpt2_lanczos_end_to_end(hlv, cuda_dev, golden_dir):
+    """HVP by double-backward on the GPU + libhlv recurrence vs oracle HVP + oracle recurrence on the CPU."""
+    g = np.load(os.path.join(golden_dir, "tiny_gpt2_hvp.npz"))
+    model_cpu = _tiny_model(g)
+    model = _tiny_model(g).to(cuda_dev)
+    ids = torch.from_numpy(g["ids"])
+    v0 = torch.from_numpy(g["vec"])
+    m = 20
+    op = hlv.HessianVectorProduct(model, [ids.to(cuda_dev)])
+    res = hlv.lanczos(op, m, v0.to(cuda_dev), reorth="full")
+    ref = oracle.lanczos_cgs2(lambda v: oracle.hess_vec(v, ids, model_cpu), v0, m, reorth="full")
+    scale = float(ref["T"].abs().max())
+    assert _rel(res.alphas, ref["alphas"], scale) < 1e-4     # HVP itself differs CPU vs GPU at ~1e-6; amplified by Lanczos
+    assert _rel(res.betas, ref["betas"], scale) < 1e-4
+    ev_ref = torch.linalg.eigvalsh(ref["T"].double())
+    assert abs(float(res.eigvals[-1]) - float(ev_ref[-1])) / scale < 1e-4
+    assert abs(float(res.eigvals[0]) - float(ev_ref[0])) / scale < 1e-4
+
+
+def test_resnet_like_odd_length_operator(hlv, cuda_dev):
+    """A conv net with BatchNorm: odd total parameter count (ragged tails everywhere), criterion loss,
+    BN in train mode as train_savespec.py:70-72."""
+    import torch.nn as nn
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Conv2d(3, 5, 3, padding=1), nn.BatchNorm2d(5), nn.ReLU(), nn.AdaptiveAvgPool2d(2),
+                        nn.Flatten(), nn.Linear(20, 7))
+    P = sum(p.numel() for p in net.parameters())
+    assert P % 4 != 0
+    x, y = torch.randn(6, 3, 8, 8), torch.randint(0, 7, (6,))
+    crit = nn.CrossEntropyLoss()
+    import copy
+    net_cpu = copy.deepcopy(net)
+    net.to(cuda_dev)
+    torch.manual_seed(2)
+    v0 = torch.randn(P)
+    v0 /= v0.norm()
+
+    def cpu_hvp(v):
+        params = list(net_cpu.parameters())
+        net_cpu.eval()
+        for mod in net_cpu.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.train()
+        loss = crit(net_cpu(x), y)
+        grads = torch.autograd.grad(loss, params, create_graph=True)
+        s = sum((vv * gg).sum() for vv, gg in zip(oracle.split_like(v, params), grads))
+        hv = torch.autograd.grad(s, params)
+        return oracle.flatten_tensors(hv)
+    op = hlv.HessianVectorProduct(net, [(x.to(cuda_dev), y.to(cuda_dev))], loss_fn=hlv.criterion_loss(crit), bn_train_mode=True)
+    m = 10
+    res = hlv.lanczos(op, m, v0.to(cuda_dev), reorth="full")
+    ref = oracle.lanczos_cgs2(cpu_hvp, v0, m, reorth="full")
+    scale = float(ref["T"].abs().max())
+    assert _rel(res.T, ref["T"], scale) < 1e-4
+
+
+def test_multi_gpu_invariance_if_available(hlv, cuda_dev, tmp_path):
+    """2-rank NCCL run (basis sharded along P, batch-sharded operator) reproduces the 1-rank T."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    worker = tmp_path / "w.py"
+    worker.write_text(r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["HLV_ROOT"])
+import hessian_llm_vision_b200 as hlv
+rank = int(os.environ["RANK"]); torch.cuda.set_device(rank)
+dist.init_process_group("nccl", init_method="tcp://127.0.0.1:" + os.environ["HLV_PORT"], rank=rank, world_size=2)
+n, m = 100_003, 30
+torch.manual_seed(0)
+d = torch.randn(2, n) * 1.5; v = torch.randn(n); v0 = (v / v.norm()).cuda()
+mine = (d[rank] / 2).cuda()
+res = hlv.lanczos(lambda q: mine * q, m, v0, reorth="full", comm=hlv.Comm())
+if rank == 0: torch.save(res.T, os.environ["HLV_OUT"])
+dist.barrier(); dist.destroy_process_group()
+''')
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = tmp_path / "T.pt"
+    procs = [subprocess.Popen([sys.executable, str(worker)], env=dict(os.environ, RANK=str(r), HLV_ROOT=root, HLV_PORT=str(port), HLV_OUT=str(out)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    for p in procs:
+        o, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, o.decode()[-2000:]
+    T2 = torch.load(out)
+    torch.manual_seed(0)
+    d = torch.randn(2, 100_003) * 1.5
+    v = torch.randn(100_003)
+    v0 = (v / v.norm()).to(cuda_dev)
+    dm = d.mean(0).to(cuda_dev)
+    res1 = hlv.lanczos(lambda q: dm * q, 30, v0, reorth="full")
+    assert _rel(T2, res1.T, float(res1.T.abs().max())) < 1e-6
