@@ -12,10 +12,10 @@ basis row, normalise + store.  The m=100 run has basis depth j = 0..99; with --s
 the timed region IS that run; with another K, step i runs at depth floor((i+0.5)*100/K) over a
 pre-built orthonormal basis so the mean depth (hence mean cost) is that of the m=100 run.
 
-Scaling is STRONG: the global batch (64 sequences x 512 tokens = 8 per GPU at 8 GPUs, micro-batch
-8 = the reference's batch size) and therefore the operator and T are the same at every N; ranks
-shard the micro-batches (reduce-scatter of Hv) and the basis along the parameter dimension
-(k-float all-reduces).  One JSON line is printed by rank 0.
+Scaling is STRONG: the global batch (8 sequences x 512 tokens, the batch of the reference's logged
+runs) and therefore the operator and T are the same at every N; ranks shard the sequences
+(reduce-scatter of Hv) and the basis along the parameter dimension (k-float all-reduces).
+One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 
@@ -47,8 +47,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--global-batch", type=int, default=64)
-    ap.add_argument("--micro-batch", type=int, default=8)
+    ap.add_argument("--global-batch", type=int, default=8, help="sequences in the Hessian's batch (reference's logged runs: 8)")
+    ap.add_argument("--micro-batch", type=int, default=0, help="sequences per double-backward; 0 = min(8, global_batch/ranks)")
+    ap.add_argument("--prefill", default="lanczos", choices=["lanczos", "random"],
+                    help="how the depth-100 basis is built before a sampled-depth run (random: no kernels; for short profiling runs)")
     ap.add_argument("--basis-dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -290,7 +292,14 @@ def run_ours(args, rank, world, local_rank):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms.item()), kernels.launch_count - launches0, (clocks.stop() if rank == 0 else None), eng.phases.summary()
 
-    prefill()
+    if args.prefill == "random" and not real_run:
+        g = torch.Generator(device=dev).manual_seed(11)
+        for r in range(M_DEPTH):                           # timing does not depend on the values
+            eng.basis[r].copy_(torch.randn(eng.basis.shape[1], device=dev, generator=g) * (1.0 / eng.basis.shape[1] ** 0.5))
+        if world > 1:
+            eng.v_full.normal_(generator=g).mul_(1.0 / n ** 0.5)
+    else:
+        prefill()
     eng.hvp = op_dev
     for i in range(max(args.warmup, 0)):
         eng.step(sched[i % len(sched)])
@@ -374,6 +383,8 @@ def run_ours(args, rank, world, local_rank):
 def main():
     args = parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.micro_batch <= 0:
+        args.micro_batch = max(1, min(8, args.global_batch // max(world if args.impl == "ours" else 1, 1)))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

@@ -55,7 +55,8 @@ def _basis(V: torch.Tensor, rows: int, n: int, name: str):
         raise ValueError(f"{name}: basis must be 2-D with unit stride along the parameter dimension")
     if V.shape[0] < rows or V.shape[1] < n:
         raise ValueError(f"{name}: basis shape {tuple(V.shape)} smaller than rows={rows}, n={n}")
-    ldv = V.stride(0) if V.shape[0] > 1 else max(V.shape[1], n)
+    # a single row has no meaningful pitch: hand the library any aligned value >= n
+    ldv = V.stride(0) if V.shape[0] > 1 else (max(V.shape[1], n) + 7) // 8 * 8
     return V.data_ptr(), ldv, sfx
 
 
@@ -228,5 +229,5 @@ def ritz_vectors(Q: torch.Tensor, m: int, Y: torch.Tensor, out: torch.Tensor, n:
         raise ValueError("ritz_vectors: out must be [nvec, >=n]")
     with torch.cuda.device(out.device):
         _lib.call(f"hlv_ritz_vectors_{sfx}", p, ldq, int(m), _cuda(Y, torch.float32, "Y"), Y.stride(0), int(nvec),
-                  out.data_ptr(), out.stride(0) if out.shape[0] > 1 else max(out.shape[1], n), int(n), _stream())
+                  out.data_ptr(), out.stride(0) if out.shape[0] > 1 else (max(out.shape[1], n) + 7) // 8 * 8, int(n), _stream())
     launch_count += (nvec + 7) // 8
