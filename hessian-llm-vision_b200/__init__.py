@@ -17,3 +17,4 @@ __version__ = "0.1.0"
 def library_path() -> str:
     from . import _lib
     return _lib.LIB_PATH
+from .spectra import SLQResult, per_block_spectra, probe_vector, slq  # noqa: F401,E402

@@ -352,6 +352,42 @@ class LanczosEngine:
                 ph.stop("all_gather")
         self.j = j + 1
 
+    # -- checkpoint / resume ---------------------------------------------------------
+    def state_dict(self, include_basis: bool = True) -> Dict[str, Any]:
+        """Everything needed to continue at iteration ``self.j``: (T so far, j, v_j, v_{j-1}[, rows
+        0..j of the basis]) as CPU tensors (local shard when sharded).  The reference only ever
+        WRITES T per iteration (diego_pythia.py:192) and cannot resume."""
+        j = self.j
+        sd: Dict[str, Any] = {"j": j, "n": self.n, "m": self.m, "reorth": self.reorth,
+                              "basis_dtype": str(self.basis_dtype), "world": self.comm.world, "rank": self.comm.rank,
+                              "alphas": self.alphas.cpu(), "betas": self.betas.cpu(),
+                              "breakdown_iter": self.breakdown_iter.cpu()}
+        if j < self.m:
+            sd["v_cur"] = self._v_shard(j).float().cpu()
+            if j > 0:
+                sd["v_prev"] = self._v_shard(j - 1).float().cpu()
+        if include_basis and self.keep_basis:
+            sd["basis_rows"] = self.basis[: min(j + 1, self.m)].cpu()
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        if (sd["n"], sd["m"], sd["world"], sd["rank"]) != (self.n, self.m, self.comm.world, self.comm.rank):
+            raise ValueError("checkpoint does not match this engine (n, m, world, rank)")
+        if self.keep_basis and "basis_rows" not in sd:
+            raise ValueError("engine keeps a basis but the checkpoint has none")
+        j = int(sd["j"])
+        self.alphas.copy_(sd["alphas"]); self.betas.copy_(sd["betas"]); self.breakdown_iter.copy_(sd["breakdown_iter"])
+        if self.keep_basis:
+            rows = sd["basis_rows"]
+            self.basis[: rows.shape[0]].copy_(rows)
+        if not self.fp32_rows and j < self.m:
+            self.ring[j & 1].copy_(sd["v_cur"])
+            if j > 0:
+                self.ring[(j - 1) & 1].copy_(sd["v_prev"])
+        if self.comm.world > 1 and j < self.m:
+            self.comm.all_gather(self.v_full, self._v_shard(j))
+        self.j = j
+
     # -- host read-back -----------------------------------------------------------
     def broke_down(self) -> int:
         """Iteration index at which beta fell below breakdown_tol, or -1 (synchronises)."""

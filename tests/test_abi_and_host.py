@@ -233,3 +233,52 @@ def test_sharded_engine_two_ranks_gloo(tmp_path, reorth, n):
     assert got["m"] == 14
     assert got["n_local"] == ((n + 1) // 2 + 7) // 8 * 8
     assert float((got["T"] - ref["T"]).abs().max()) / scale < (2e-5 if reorth else 2e-3)
+
+
+# ---------------------------------------------------------------- resume, SLQ, per-block (host logic, test double)
+def test_checkpoint_resume_matches_uninterrupted_run():
+    import hessian_llm_vision_b200 as hlv
+    M, v0 = _sym(8, 120)
+    m = 16
+    for reorth, dt in ((None, torch.float32), ("full", torch.float32), ("full", torch.bfloat16)):
+        full = hlv.lanczos(lambda v: M @ v, m, v0, reorth=reorth, basis_dtype=dt, ops=fake_ops)
+        a = hlv.LanczosEngine(lambda v: M @ v, 120, m, "cpu", reorth=reorth, basis_dtype=dt, ops=fake_ops)
+        a.start(v0)
+        for j in range(7):
+            a.step(j)
+        sd = a.state_dict()
+        b = hlv.LanczosEngine(lambda v: M @ v, 120, m, "cpu", reorth=reorth, basis_dtype=dt, ops=fake_ops)
+        b.load_state_dict(sd)
+        assert b.j == 7
+        for j in range(7, m):
+            b.step(j)
+        assert torch.equal(b.result().T, full.T)
+
+
+def test_slq_multi_probe_and_block_drivers(golden_dir):
+    import hessian_llm_vision_b200 as hlv
+    M, _ = _sym(2, 200)
+    r = hlv.slq(lambda v: M @ v, 200, 20, seeds=[0, 1, 2, 3], device="cpu", ops=fake_ops)
+    assert r.seeds == [0, 1, 2, 3] and len(r.eigvals) == 4
+    d = r.eigeninfo()
+    assert abs(float(d["gammas"].sum()) - 1) < 1e-5 and bool((d["eigvals"][1:] >= d["eigvals"][:-1]).all())
+    grid, dens = r.density(num_points=2000, margin=0.3)
+    assert abs(np.trapezoid(dens, grid) - 1) < 2e-2
+    # trace estimate: E[v^T H v] = sum_i gamma_i lambda_i ~ tr(H)/n
+    est = float((d["eigvals"] * d["gammas"]).sum())
+    assert abs(est - float(torch.trace(M)) / 200) < 0.5
+    # each probe equals a plain lanczos() run from the same probe vector
+    one = hlv.lanczos(lambda v: M @ v, 20, hlv.probe_vector(200, 2, "cpu"), reorth="full", ops=fake_ops)
+    assert torch.equal(one.eigvals, r.eigvals[2])
+    # per-block spectra on the tiny golden GPT-2 (visual-eigen.ipynb cell 12), CPU test double
+    from tests.test_oracle_golden import _tiny_model_from_golden
+    g = np.load(os.path.join(golden_dir, "tiny_gpt2_hvp.npz"))
+    model = _tiny_model_from_golden(g)
+    ids = torch.from_numpy(g["ids"])
+    ev, gm = hlv.per_block_spectra(model, [ids], 4, seed=5, ops=fake_ops)
+    assert len(ev) == 2 and all(e.shape == (4,) for e in ev)
+    blk = list(model.transformer.h[1].parameters())
+    nb = sum(p.numel() for p in blk)
+    ref = oracle.lanczos_cgs2(lambda v: oracle.hess_vec_subset(v, [ids], model, blk), hlv.probe_vector(nb, 6, "cpu"), 4, reorth="full")
+    ev_ref = torch.linalg.eigvalsh(ref["T"].double())
+    assert float((ev[1].double() - ev_ref).abs().max()) < 1e-4 * float(ev_ref.abs().max())
