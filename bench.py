@@ -135,11 +135,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel: str):
+def ncu_traffic(kernel: str, algorithmic_bytes_per_launch: float):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
+    capture (profiles/roofline_traffic.json): the captured launch's traffic/algorithmic ratio applied to this
+    run's mean algorithmic bytes per launch (the basis depth differs from launch to launch)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel)
+            d = json.load(open(p)).get(kernel)
+            return algorithmic_bytes_per_launch * d["dram_bytes"] / d["algorithmic_bytes"]
         except Exception:
             return None
     return None
@@ -341,14 +345,15 @@ def run_ours(args, rank, world, local_rank):
             d = phases[name]
             gbs = fn(d) / (d["ms"] * 1e-3) / 1e9
             kernels_out[name] = {"ms_total": round(d["ms"], 3), "launches": d["calls"], "achieved_gbs": round(gbs, 1),
-                                 "frac_of_peak": round(gbs / peak, 4)}
+                                 "frac_of_peak": round(gbs / peak, 4), "bytes_per_launch": fn(d) / d["calls"]}
     ours_ms = sum(v["ms_total"] for v in kernels_out.values())
     top = max((k for k in kernels_out if k.startswith("cgs")), key=lambda k: kernels_out[k]["ms_total"], default=None)
     roofline = None
     if top:
         kname = f"hlv::{top}_kernel<{'float' if s == 4 else 'bf16'}>"
         roofline = {"bound": "hbm", "kernel": kname, "achieved": kernels_out[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels_out[top]["frac_of_peak"], "traffic": ncu_traffic(top), "peak_source": peak_src,
+                    "frac": kernels_out[top]["frac_of_peak"], "bytes_per_launch": kernels_out[top]["bytes_per_launch"],
+                    "traffic": ncu_traffic(top, kernels_out[top]["bytes_per_launch"]), "peak_source": peak_src,
                     "bytes_model": "project: (rows*s+4)*n per launch; update: (rows*s+8)*n per launch (DESIGN.md)",
                     "share_of_step": round(kernels_out[top]["ms_total"] / ms, 4)}
     line = {"metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -300,7 +300,7 @@ static int project(const char* name, const BT* V, int64_t ldv, int rows, const f
                                              kWarps * HLV_MAX_ROWS * (int)sizeof(double));
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(project)");
     }
-    const int grid = persistent_grid((n + kTile - 1) / kTile, 2);
+    const int grid = persistent_grid((n + kTile - 1) / kTile, resident_ctas(cgs_project_kernel<BT>, smem));
     cgs_project_kernel<BT><<<grid, kThreads, smem, stream>>>(V, ldv, rows, w, n, ws.partials, ws.counters, c_out);
     HLV_LAUNCH_CHECK(name);
     return HLV_OK;
@@ -315,7 +315,7 @@ static int update(const char* name, const BT* V, int64_t ldv, int rows, const do
     Workspace ws{};
     if (norm2_out)
         HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, 1, &ws), HLV_ERR_WORKSPACE, "%s: workspace too small", name);
-    const int grid = persistent_grid((n + kTile - 1) / kTile, 2);
+    const int grid = persistent_grid((n + kTile - 1) / kTile, resident_ctas(cgs_update_kernel<BT>, rows * sizeof(float)));
     cgs_update_kernel<BT><<<grid, kThreads, rows * sizeof(float), stream>>>(V, ldv, rows, c, sign, w, n, ws.partials,
                                                                            ws.counters, norm2_out);
     HLV_LAUNCH_CHECK(name);
@@ -331,7 +331,7 @@ static int ritz_vectors(const char* name, const BT* Q, int64_t ldq, int m, const
     HLV_REQUIRE(aligned16(Q) && aligned16(out) && ((ldq * (int64_t)sizeof(BT)) & 15) == 0 && ((ldo * 4) & 15) == 0,
                 HLV_ERR_ALIGN, "%s: Q, out must be 16-byte aligned with 16-byte row pitch", name);
     HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "%s: no CUDA device", name);
-    const int grid = persistent_grid((n + kTile - 1) / kTile, 2);
+    const int grid = persistent_grid((n + kTile - 1) / kTile, resident_ctas(ritz_vectors_kernel<BT>, (size_t)m * kNv * sizeof(float)));
     for (int v0 = 0; v0 < nvec; v0 += kNv) {
         const int nv = nvec - v0 < kNv ? nvec - v0 : kNv;
         ritz_vectors_kernel<BT><<<grid, kThreads, (size_t)m * kNv * sizeof(float), stream>>>(Q, ldq, m, Y, ldy, v0, nv,

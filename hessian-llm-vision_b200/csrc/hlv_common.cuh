@@ -70,6 +70,18 @@ int sm_count();                                  // cached per device, <=0 on fa
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Resident CTAs per SM of `kernel` (kThreads threads, `smem` dynamic bytes) from the occupancy API, so a
+// persistent grid is exactly ONE resident wave: no second, under-filled wave and no tail.
+template <typename Kernel>
+inline int resident_ctas(Kernel kernel, size_t smem = 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 1;
+    }
+    return per_sm;
+}
+
 // Persistent grid: one resident wave, capped by the amount of work.
 inline int persistent_grid(int64_t work_items, int ctas_per_sm) {
     int64_t g = (int64_t)sm_count() * ctas_per_sm;

@@ -160,8 +160,14 @@ static int launch_multi_tensor(const void* const* h_ptr, const int64_t* h_numel,
         }
         return HLV_OK;
     }
-    const int grid = persistent_grid((total + kChunk - 1) / kChunk, 8);
     const bool plain = (scale == 1.0f && !accumulate);
+    int per_sm;
+    if (!GATHER) per_sm = resident_ctas(multi_tensor_kernel<CAP, false, kCopy, false>);
+    else if (dot_out) per_sm = plain ? resident_ctas(multi_tensor_kernel<CAP, true, kCopy, true>)
+                                     : resident_ctas(multi_tensor_kernel<CAP, true, kScaleAcc, true>);
+    else per_sm = plain ? resident_ctas(multi_tensor_kernel<CAP, true, kCopy, false>)
+                        : resident_ctas(multi_tensor_kernel<CAP, true, kScaleAcc, false>);
+    const int grid = persistent_grid((total + kChunk - 1) / kChunk, per_sm);
     if (!GATHER) {
         multi_tensor_kernel<CAP, false, kCopy, false><<<grid, kThreads, 0, stream>>>(
             tab, flat, nullptr, 1.0f, 0, nullptr, nullptr, nullptr);
@@ -343,9 +349,7 @@ normalize_store_kernel(const float* __restrict__ w, const double* __restrict__ n
     }
     const int64_t n8 = n >> 3;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n8; i += stride) {
-        float4 x0 = ldg_stream(reinterpret_cast<const float4*>(w) + 2 * i);
-        float4 x1 = ldg_stream(reinterpret_cast<const float4*>(w) + 2 * i + 1);
+    auto emit = [&](int64_t i, float4 x0, float4 x1) {
         x0.x = __fdiv_rn(x0.x, beta); x0.y = __fdiv_rn(x0.y, beta); x0.z = __fdiv_rn(x0.z, beta); x0.w = __fdiv_rn(x0.w, beta);
         x1.x = __fdiv_rn(x1.x, beta); x1.y = __fdiv_rn(x1.y, beta); x1.z = __fdiv_rn(x1.z, beta); x1.w = __fdiv_rn(x1.w, beta);
         if (v_out != nullptr) {
@@ -360,7 +364,16 @@ normalize_store_kernel(const float* __restrict__ w, const double* __restrict__ n
             o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
             reinterpret_cast<uint4*>(row_bf16)[i] = o;
         }
+    };
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    for (; i + stride < n8; i += 2 * stride) {             // 4 independent 128-bit loads in flight per thread
+        float4 a0 = ldg_stream(w4 + 2 * i), a1 = ldg_stream(w4 + 2 * i + 1);
+        float4 b0 = ldg_stream(w4 + 2 * (i + stride)), b1 = ldg_stream(w4 + 2 * (i + stride) + 1);
+        emit(i, a0, a1);
+        emit(i + stride, b0, b1);
     }
+    for (; i < n8; i += stride) emit(i, ldg_stream(w4 + 2 * i), ldg_stream(w4 + 2 * i + 1));
     const int64_t t = (n8 << 3) + (int64_t)blockIdx.x * kThreads + threadIdx.x;      // ragged tail (< 8 elements)
     if (t < n) {
         float x = __fdiv_rn(w[t], beta);
@@ -399,7 +412,8 @@ int hlv_dot_f32(const float* a, const float* b, int64_t n, double* out, void* ws
     Workspace ws;
     HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, 1, &ws), HLV_ERR_WORKSPACE, "hlv_dot_f32: workspace too small");
     HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "hlv_dot_f32: no CUDA device");
-    const int grid = persistent_grid((n / 4 + kThreads * kVecPerThread - 1) / (kThreads * kVecPerThread) + 1, 8);
+    const int grid = persistent_grid((n / 4 + kThreads * kVecPerThread - 1) / (kThreads * kVecPerThread) + 1,
+                                     resident_ctas(dot_kernel));
     dot_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, ws.partials, ws.counters, out);
     HLV_LAUNCH_CHECK("hlv_dot_f32 launch");
     return HLV_OK;
@@ -416,7 +430,8 @@ int hlv_lanczos_update_f32(float* w, const float* vj, const float* vjm1, const d
     Workspace ws;
     HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, 1, &ws), HLV_ERR_WORKSPACE, "hlv_lanczos_update_f32: workspace too small");
     HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "hlv_lanczos_update_f32: no CUDA device");
-    const int grid = persistent_grid((n / 4 + kThreads * kVecPerThread - 1) / (kThreads * kVecPerThread) + 1, 4);
+    const int grid = persistent_grid((n / 4 + kThreads * kVecPerThread - 1) / (kThreads * kVecPerThread) + 1,
+                                     vjm1 ? resident_ctas(lanczos_update_kernel<true>) : resident_ctas(lanczos_update_kernel<false>));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (vjm1)
         lanczos_update_kernel<true><<<grid, kThreads, 0, s>>>(w, vj, vjm1, alpha, beta, n, ws.partials, ws.counters, norm2_out);
@@ -435,7 +450,8 @@ int hlv_normalize_store_f32(const float* w, const double* norm2, int64_t n, doub
     HLV_REQUIRE(aligned16(w) && aligned16(v_out) && aligned16(row_bf16), HLV_ERR_ALIGN,
                 "hlv_normalize_store_f32: vectors must be 16-byte aligned");
     HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "hlv_normalize_store_f32: no CUDA device");
-    const int grid = persistent_grid((n / 8 + kThreads - 1) / kThreads + 1, 8);
+    const int grid = persistent_grid((n / 8 + kThreads * 2 - 1) / (kThreads * 2) + 1,
+                                     row_bf16 ? resident_ctas(normalize_store_kernel<true>) : resident_ctas(normalize_store_kernel<false>));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (row_bf16)
         normalize_store_kernel<true><<<grid, kThreads, 0, s>>>(w, norm2, n, beta_out, v_out, row_bf16,

@@ -1,5 +1,10 @@
-"""GPU probe (dev tool): time the GPT-2 124M HVP per micro-batch, memory, cached-graph variant."""
-import os, sys, time, json
+"""GPU probe (dev tool): time the GPT-2 124M HVP per micro-batch: eager launches, cached first-backward
+graph, and CUDA-graph replay; checks the variants agree."""
+import json
+import os
+import sys
+import time
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
@@ -11,23 +16,50 @@ model, cfg = bench.build_model(False)
 model.to(dev)
 n = sum(p.numel() for p in model.parameters())
 out = {"P": n}
-v = torch.randn(n, device=dev); v /= v.norm()
+v = torch.randn(n, device=dev)
+v /= v.norm()
 w = torch.empty(n, device=dev)
-for B in (1, 2, 4, 8, 16):
+batches = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "1,2,4,8".split(","))]
+
+
+def timeit(fn, reps=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, (time.perf_counter() - t0) * 1e3 / reps
+
+
+for B in batches:
     ids = bench.make_tokens(cfg, B, B, 512)[0].to(dev)
-    for cache in (False, True):
-        torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
-        op = hlv.HessianVectorProduct(model, [ids], cache_graph=cache)
-        for _ in range(2):
-            op.accumulate_into(v, w)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            op.accumulate_into(v, w)
-        e1.record(); torch.cuda.synchronize()
-        out[f"B{B}_cache{int(cache)}"] = {"gpu_ms": e0.elapsed_time(e1) / 5, "wall_ms": (time.perf_counter() - t0) * 200,
-                                          "peak_gb": torch.cuda.max_memory_allocated() / 2**30}
-        op.clear_cache(); del op
-        print(B, cache, out[f"B{B}_cache{int(cache)}"], flush=True)
+    ref = None
+    for variant in ("eager", "cache", "cudagraph"):
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        try:
+            op = hlv.HessianVectorProduct(model, [ids], cache_graph=(variant == "cache"))
+            run_op = op.capture() if variant == "cudagraph" else op
+            gpu_ms, wall_ms = timeit(lambda: run_op.accumulate_into(v, w))
+            if ref is None:
+                ref = w.clone()
+                err = 0.0
+            else:
+                err = float((w - ref).abs().max() / ref.abs().max())
+            out[f"B{B}_{variant}"] = {"gpu_ms": gpu_ms, "wall_ms": wall_ms, "peak_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                                      "rel_err_vs_eager": err}
+        except Exception as e:  # noqa: BLE001
+            out[f"B{B}_{variant}"] = {"error": repr(e)[:400]}
+        print(B, variant, out[f"B{B}_{variant}"], flush=True)
+        try:
+            op.clear_cache()
+            del run_op, op
+        except Exception:  # noqa: BLE001
+            pass
+os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/hvp_probe.json", "w"), indent=1)
