@@ -364,6 +364,7 @@ def run_ours(args, rank, world, local_rank):
             "recurrence_only": {"ms_per_step": ours_ms / args.steps, "iterations_per_s": args.steps / (ours_ms / 1e3) if ours_ms else None,
                                 "note": "sum of libhlv kernel time (CUDA events) in the timed region; HVP (torch) excluded"},
             "hvp_ms_per_step": phases.get("hvp", {}).get("ms", 0.0) / args.steps,
+            "phases_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in phases.items()},
             "ritz_top3": ritz_top}
     # ---- CPU baseline: the reference's CPU path on this box's host cores (rank 0, N=1 only) ----
     if world == 1 and not args.no_cpu_baseline:

@@ -43,7 +43,9 @@ for B in batches:
         torch.cuda.empty_cache()
         torch.cuda.reset_peak_memory_stats()
         try:
-            op = hlv.HessianVectorProduct(model, [ids], cache_graph=(variant == "cache"))
+            # cudagraph: first-backward graph built eagerly once (HF forward code is not capturable: it copies
+            # CPU scalars to the device), the second backward + gather are captured and replayed
+            op = hlv.HessianVectorProduct(model, [ids], cache_graph=(variant in ("cache", "cudagraph")))
             run_op = op.capture() if variant == "cudagraph" else op
             gpu_ms, wall_ms = timeit(lambda: run_op.accumulate_into(v, w))
             if ref is None:
