@@ -56,7 +56,8 @@ for B in batches:
             out[f"B{B}_{variant}"] = {"gpu_ms": gpu_ms, "wall_ms": wall_ms, "peak_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
                                       "rel_err_vs_eager": err}
         except Exception as e:  # noqa: BLE001
-            out[f"B{B}_{variant}"] = {"error": repr(e)[:400]}
+            import traceback
+            out[f"B{B}_{variant}"] = {"error": repr(e)[:400], "traceback": traceback.format_exc()[-3000:]}
         print(B, variant, out[f"B{B}_{variant}"], flush=True)
         try:
             op.clear_cache()
