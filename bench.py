@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--basis-dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="CGS2 as 4 separate passes (project, update, project, update)")
     ap.add_argument("--extras", action="store_true", help="also time the cached / CUDA-graph HVP modes (reported under 'extras')")
     ap.add_argument("--cache-graph", action="store_true", help="keep the first-backward graph across iterations (extra, not the headline)")
     ap.add_argument("--small", action="store_true", help="tiny model for a functional check of this script (NOT a benchmark)")
@@ -257,7 +258,8 @@ def run_ours(args, rank, world, local_rank):
     op_dev = hlv.HessianVectorProduct(model, mine_dev, total_sequences=args.global_batch, cache_graph=args.cache_graph)
     op_host = hlv.HessianVectorProduct(model, mine_host, total_sequences=args.global_batch, device=dev)
     basis_dtype = torch.float32 if args.basis_dtype == "f32" else torch.bfloat16
-    eng = hlv.LanczosEngine(op_dev, n, M_DEPTH, dev, reorth="full", basis_dtype=basis_dtype, comm=comm, profile=True)
+    eng = hlv.LanczosEngine(op_dev, n, M_DEPTH, dev, reorth="full", basis_dtype=basis_dtype, comm=comm, profile=True,
+                            fused_cgs=not args.no_fused)
     torch.manual_seed(7)                                  # probe: randn(P)/norm, diego_pythia.py:147-149
     v0 = torch.randn(n)
     v0 = (v0 / v0.norm()).to(dev)
@@ -357,6 +359,7 @@ def run_ours(args, rank, world, local_rank):
     kern_bytes = {
         "cgs_project": lambda d: (d["rows"] * s + 4 * d["calls"]) * n_loc,
         "cgs_update": lambda d: (d["rows"] * s + 8 * d["calls"]) * n_loc,
+        "cgs_update_project": lambda d: (d["rows"] * s + 8 * d["calls"]) * n_loc,   # V once; w read + written
         "update": lambda d: 16 * n_loc * d["calls"],
         "normalize": lambda d: (4 + s) * n_loc * d["calls"] if s == 4 else (4 + 4 + s) * n_loc * d["calls"],
         "gather": lambda d: (8 + 4) * n * d["calls"],      # read pieces 4n + write w 4n (+4n v for the fused alpha on the last micro-batch)

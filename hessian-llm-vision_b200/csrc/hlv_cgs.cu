@@ -7,7 +7,7 @@
 //
 // Work decomposition ("column owner"): a CTA owns column tiles of kTile consecutive elements;
 // per tile it keeps its slice of w in registers and streams the `rows` basis rows of that tile
-// past it, kRowBatch rows (= 2*kRowBatch independent 128-bit loads per thread) at a time.
+// past it, 8 fp32 / 16 bf16 rows (= 16 independent 128-bit loads per thread) at a time.
 // V is read exactly once per pass, w once (project) or once + one write (update).
 // Arithmetic intensity is 0.5 flop/byte (fp32 basis) -- HBM roofline, no tensor cores.
 #include "hlv_common.cuh"
@@ -16,7 +16,8 @@ namespace hlv {
 
 constexpr int kEpt = 8;                         // elements of w per thread per tile
 constexpr int kTile = kThreads * kEpt;          // 2048 columns per tile (8 KB of an fp32 row)
-constexpr int kRowBatch = 8;                    // rows whose loads are in flight together
+// rows whose loads are in flight together: 16 x 128-bit loads per thread for either storage type
+template <typename BT> __host__ __device__ constexpr int row_batch() { return sizeof(BT) == 2 ? 16 : 8; }
 
 // ---- per-thread slice of one basis row: 8 consecutive-by-4 elements ---------------------
 // Element layout inside a tile keeps every 128-bit access fully coalesced:
@@ -108,6 +109,7 @@ cgs_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const float*
                    double* partials, unsigned* counter, double* c_out) {
     extern __shared__ double s_acc[];                   // [kWarps][rows_pad]: per-warp running sums
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kRowBatch = row_batch<BT>();
     const int rows_pad = (rows + kRowBatch - 1) / kRowBatch * kRowBatch;
     for (int i = tid; i < kWarps * rows_pad; i += kThreads) s_acc[i] = 0.0;
     __syncthreads();
@@ -140,8 +142,11 @@ cgs_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const float*
                     for (int e = 0; e < 8; ++e) p[i] = fmaf(x[e], wv[e], p[i]);
                 }
             }
-            const float tot = warp_sum8(p, lane);
-            if ((lane & 3) == 0) my_acc[r0 + my_row] += (double)tot;   // rows_pad covers r0+my_row
+#pragma unroll
+            for (int h = 0; h < kRowBatch / 8; ++h) {
+                const float tot = warp_sum8(*reinterpret_cast<float(*)[8]>(p + 8 * h), lane);
+                if ((lane & 3) == 0) my_acc[r0 + 8 * h + my_row] += (double)tot;   // rows_pad covers the index
+            }
         }
     }
     __syncthreads();
@@ -164,6 +169,7 @@ cgs_update_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const double*
     extern __shared__ float s_c[];                      // sign * (float)c[i]
     __shared__ double s_warp[kWarps];
     const int tid = threadIdx.x;
+    constexpr int kRowBatch = row_batch<BT>();
     for (int i = tid; i < rows; i += kThreads) s_c[i] = sign * (float)c[i];
     __syncthreads();
     float nrm = 0.0f;
@@ -293,11 +299,11 @@ static int project(const char* name, const BT* V, int64_t ldv, int rows, const f
     Workspace ws;
     HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, rows, &ws), HLV_ERR_WORKSPACE,
                 "%s: workspace too small for %d rows (need %zu bytes)", name, rows, workspace_bytes(rows));
-    const int rows_pad = (rows + kRowBatch - 1) / kRowBatch * kRowBatch;
+    const int rows_pad = (rows + row_batch<BT>() - 1) / row_batch<BT>() * row_batch<BT>();
     const size_t smem = (size_t)kWarps * rows_pad * sizeof(double);
     if (smem > 48 * 1024) {                             // only for rows > 768; per-device attribute
         cudaError_t e = cudaFuncSetAttribute(cgs_project_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kWarps * HLV_MAX_ROWS * (int)sizeof(double));
+                                             kWarps * (HLV_MAX_ROWS + 16) * (int)sizeof(double));
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(project)");
     }
     const int grid = persistent_grid((n + kTile - 1) / kTile, resident_ctas(cgs_project_kernel<BT>, smem));

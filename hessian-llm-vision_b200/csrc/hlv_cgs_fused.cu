@@ -1,0 +1,376 @@
+// libhlv.so -- kernel (c'), the middle pass of CGS2 fused:   w' = w - V^T c1 ;  c2 = V w' ;  |w'|^2
+// reading V from HBM ONCE instead of twice.
+//
+// Two-pass classical Gram-Schmidt is project, update, project, update = 4 streaming passes over the
+// basis.  The 2nd and 3rd touch the same data in the same order, and the 3rd needs nothing global from
+// the 2nd (w' is complete per column as soon as all rows of that column have been applied).  On B200 a
+// CTA can hold a whole [rows x TW] column slab of the basis in its 227 KB of shared memory (100 fp32 rows
+// x 512 columns = 200 KB), so: apply the update from the slab as its rows land (pass A), then project the
+// finished w' tile against the SAME slab (pass B).  CGS2 becomes 3 passes: (3*j*s + 20)*n bytes
+// instead of (4*j*s + 24)*n.
+//
+// Data movement is TMA: one elected producer thread issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP)
+// row by row into the slab; completion is tracked by mbarriers (one per group of 8 rows so a consumer
+// pays one try_wait per 8 rows), and each row's slot is handed back to the producer the moment pass B
+// has consumed it, so the next tile's loads are in flight while this tile is still being projected.
+// 8 consumer warps: pass A "thread owns columns", pass B "warp owns rows" (fixed-order reductions).
+#include "hlv_common.cuh"
+
+namespace hlv {
+
+constexpr int kFusedConsumers = 256;
+constexpr int kFusedThreads = kFusedConsumers + 32;      // + one producer warp
+constexpr int kGroup = 8;                                // rows per mbarrier
+constexpr int kFusedSlabBytes = 200 * 1024;
+
+// ---- mbarrier / TMA (1-D bulk) PTX ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kFusedConsumers) : "memory"); }
+
+template <typename BT> __device__ __forceinline__ float elem_to_float(BT x);
+template <> __device__ __forceinline__ float elem_to_float<float>(float x) { return x; }
+template <> __device__ __forceinline__ float elem_to_float<uint16_t>(uint16_t x) { return __uint_as_float((uint32_t)x << 16); }
+
+// 16 bytes of a slab row -> floats (4 fp32 or 8 bf16)
+template <typename BT> struct Chunk16;
+template <> struct Chunk16<float> {
+    static constexpr int kElems = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&x)[8]) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
+};
+template <> struct Chunk16<uint16_t> {
+    static constexpr int kElems = 8;
+    static __device__ __forceinline__ void load(const uint16_t* p, float (&x)[8]) {
+        uint4 v = *reinterpret_cast<const uint4*>(p);
+        x[0] = bf16_lo(v.x); x[1] = bf16_hi(v.x); x[2] = bf16_lo(v.y); x[3] = bf16_hi(v.y);
+        x[4] = bf16_lo(v.z); x[5] = bf16_hi(v.z); x[6] = bf16_lo(v.w); x[7] = bf16_hi(v.w);
+    }
+};
+
+// CPT consecutive slab elements of one thread -> floats, as ONE shared-memory access (conflict-free:
+// consecutive lanes read consecutive 4/8/16-byte words).
+template <typename BT, int CPT> struct SlabVec {
+    static __device__ __forceinline__ void load(const BT* p, float (&v)[CPT]) {
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) v[q] = elem_to_float<BT>(p[q]);
+    }
+};
+template <> struct SlabVec<float, 2> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[2]) {
+        float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
+    }
+};
+template <> struct SlabVec<float, 4> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+template <> struct SlabVec<uint16_t, 2> {
+    static __device__ __forceinline__ void load(const uint16_t* p, float (&v)[2]) {
+        uint32_t u = *reinterpret_cast<const uint32_t*>(p); v[0] = bf16_lo(u); v[1] = bf16_hi(u);
+    }
+};
+template <> struct SlabVec<uint16_t, 4> {
+    static __device__ __forceinline__ void load(const uint16_t* p, float (&v)[4]) {
+        uint2 u = *reinterpret_cast<const uint2*>(p);
+        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    }
+};
+template <> struct SlabVec<uint16_t, 8> {
+    static __device__ __forceinline__ void load(const uint16_t* p, float (&v)[8]) {
+        uint4 u = *reinterpret_cast<const uint4*>(p);
+        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+        v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+    }
+};
+// CPT consecutive floats of w / s_w as one access when the tile is full
+template <int CPT> __device__ __forceinline__ void ld_f32(const float* p, float (&v)[CPT]) {
+    if (CPT == 2) { float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1 % CPT] = t.y; }
+    else if (CPT == 4) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1 % CPT] = t.y; v[2 % CPT] = t.z; v[3 % CPT] = t.w; }
+    else if (CPT == 8) {
+        float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1 % CPT] = a.y; v[2 % CPT] = a.z; v[3 % CPT] = a.w; v[4 % CPT] = b.x; v[5 % CPT] = b.y; v[6 % CPT] = b.z; v[7 % CPT] = b.w;
+    } else { v[0] = p[0]; }
+}
+template <int CPT> __device__ __forceinline__ void st_f32(float* p, const float (&v)[CPT]) {
+    if (CPT == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1 % CPT]);
+    else if (CPT == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1 % CPT], v[2 % CPT], v[3 % CPT]);
+    else if (CPT == 8) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1 % CPT], v[2 % CPT], v[3 % CPT]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4 % CPT], v[5 % CPT], v[6 % CPT], v[7 % CPT]);
+    } else p[0] = v[0];
+}
+
+struct FusedSmem {
+    size_t slab, s_w, s_c, s_acc, bars, total;
+};
+__host__ __device__ inline FusedSmem fused_layout(int rows, int tw, int elem_bytes) {
+    FusedSmem L;
+    const int ngroups = (rows + kGroup - 1) / kGroup;
+    L.slab = 0;
+    L.s_w = (size_t)rows * tw * elem_bytes;
+    L.s_c = L.s_w + (size_t)tw * 4;
+    L.s_acc = L.s_c + (size_t)((rows + 3) / 4 * 4) * 4;
+    L.bars = L.s_acc + (size_t)rows * 8;
+    L.total = L.bars + (size_t)ngroups * 16;
+    return L;
+}
+
+template <typename BT, int CPT>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const double* __restrict__ c_in,
+                          float* __restrict__ w, int64_t n, double* partials, unsigned* counter,
+                          double* c_out, double* norm2_out) {
+    constexpr int TW = kFusedConsumers * CPT;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const FusedSmem L = fused_layout(rows, TW, (int)sizeof(BT));
+    BT* slab = reinterpret_cast<BT*>(smem + L.slab);
+    float* s_w = reinterpret_cast<float*>(smem + L.s_w);
+    float* s_c = reinterpret_cast<float*>(smem + L.s_c);
+    double* s_acc = reinterpret_cast<double*>(smem + L.s_acc);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
+    const int ngroups = (rows + kGroup - 1) / kGroup;
+    uint64_t* empty = full + ngroups;
+    __shared__ double s_warp[kWarps];
+    __shared__ unsigned s_ticket;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int g = 0; g < ngroups; ++g) {
+            const int rows_g = min(kGroup, rows - g * kGroup);
+            mbar_init(&full[g], 1);
+            mbar_init(&empty[g], rows_g);
+        }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < rows; i += kFusedThreads) {
+        s_c[i] = -(float)c_in[i];
+        s_acc[i] = 0.0;
+    }
+    __syncthreads();
+
+    const int64_t ntiles_full = n / TW;
+    const int64_t ntiles = ntiles_full + ((n % TW) ? 1 : 0);
+    float nrm = 0.0f;
+
+    if (warp == kWarps) {
+        // ===== producer: one elected lane streams row tiles into the slab =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles_full; tile += gridDim.x, ++it) {
+                const BT* col0 = V + tile * TW;
+                for (int g = 0; g < ngroups; ++g) {
+                    const int rows_g = min(kGroup, rows - g * kGroup);
+                    mbar_wait(&empty[g], (it & 1u) ^ 1u);          // slot group free (passes at once on the first tile)
+                    mbar_arrive_expect_tx(&full[g], (uint32_t)(rows_g * TW * sizeof(BT)));
+                    for (int r = 0; r < rows_g; ++r) {
+                        const int i = g * kGroup + r;
+                        tma_bulk_g2s(slab + (size_t)i * TW, col0 + (int64_t)i * ldv, (uint32_t)(TW * sizeof(BT)), &full[g]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== consumers =====
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const bool manual = tile >= ntiles_full;               // ragged last tile: filled by hand, zero padded
+            const int64_t x0 = tile * TW;
+            const int valid = (int)((n - x0 < TW) ? (n - x0) : TW);
+            float acc[CPT];
+            if (!manual) {
+                ld_f32<CPT>(w + x0 + tid * CPT, acc);
+            } else {
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) {
+                    const int x = tid * CPT + q;
+                    acc[q] = x < valid ? w[x0 + x] : 0.0f;
+                }
+            }
+            if (manual) {
+                consumer_bar();                                    // previous tile's pass B is over: slab is ours
+                for (int idx = tid; idx < rows * TW; idx += kFusedConsumers) {
+                    const int i = idx / TW, x = idx - i * TW;
+                    BT zero = BT(0);
+                    slab[idx] = x < valid ? V[(int64_t)i * ldv + x0 + x] : zero;
+                }
+                consumer_bar();
+            }
+            // ---- pass A: w' = w - sum_i c1[i] V[i, tile] ----
+            for (int g = 0; g < ngroups; ++g) {
+                if (!manual) mbar_wait(&full[g], it & 1u);
+                const int i0 = g * kGroup;
+                const int rows_g = min(kGroup, rows - i0);
+#pragma unroll
+                for (int r = 0; r < kGroup; ++r) {
+                    if (r < rows_g) {
+                        const float ci = s_c[i0 + r];
+                        float v[CPT];
+                        SlabVec<BT, CPT>::load(slab + (size_t)(i0 + r) * TW + tid * CPT, v);
+#pragma unroll
+                        for (int q = 0; q < CPT; ++q) acc[q] = fmaf(ci, v[q], acc[q]);
+                    }
+                }
+            }
+            consumer_bar();                                        // nobody still reads s_w from the previous pass B
+            if (!manual) {
+                st_f32<CPT>(w + x0 + tid * CPT, acc);
+            } else {
+#pragma unroll
+                for (int q = 0; q < CPT; ++q)
+                    if (tid * CPT + q < valid) w[x0 + tid * CPT + q] = acc[q];
+            }
+            st_f32<CPT>(s_w + tid * CPT, acc);                     // columns >= valid hold 0
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) nrm = fmaf(acc[q], acc[q], nrm);
+            consumer_bar();                                        // w' tile complete in shared memory
+            // ---- pass B: c2[i] += <V[i, tile], w'>, warp (i mod 8) owns row i ----
+            constexpr int E = Chunk16<BT>::kElems;
+            for (int i = warp; i < rows; i += kWarps) {
+                const BT* row = slab + (size_t)i * TW;
+                float p = 0.0f;
+                for (int x = lane * E; x < TW; x += 32 * E) {
+                    float v[8];
+                    Chunk16<BT>::load(row + x, v);
+                    const float4 a = *reinterpret_cast<const float4*>(s_w + x);
+                    p = fmaf(v[0], a.x, p); p = fmaf(v[1], a.y, p); p = fmaf(v[2], a.z, p); p = fmaf(v[3], a.w, p);
+                    if (E == 8) {
+                        const float4 b = *reinterpret_cast<const float4*>(s_w + x + 4);
+                        p = fmaf(v[4], b.x, p); p = fmaf(v[5], b.y, p); p = fmaf(v[6], b.z, p); p = fmaf(v[7], b.w, p);
+                    }
+                }
+                p = warp_sum(p);
+                if (lane == 0) {
+                    s_acc[i] += (double)p;
+                    if (!manual) mbar_arrive(&empty[i / kGroup]);  // hand the row's slot back to the producer
+                }
+            }
+        }
+    }
+    // ===== epilogue: per-CTA partials, then the last CTA reduces across CTAs in index order =====
+    double t = warp_sum((double)nrm);
+    if (warp < kWarps && lane == 0) s_warp[warp] = t;
+    __syncthreads();
+    for (int r = tid; r < rows; r += kFusedThreads) partials[(size_t)r * kMaxCtas + blockIdx.x] = s_acc[r];
+    if (tid == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) s += s_warp[i];
+        partials[(size_t)rows * kMaxCtas + blockIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicInc(counter, gridDim.x - 1);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    if (warp < kWarps) {
+        const int nblk = gridDim.x;
+        for (int r = warp; r <= rows; r += kWarps) {
+            const double* p = partials + (size_t)r * kMaxCtas;
+            double s = 0.0;
+            for (int b = lane; b < nblk; b += 32) s += __ldcg(p + b);
+            s = warp_sum(s);
+            if (lane == 0) {
+                if (r < rows) c_out[r] = s; else norm2_out[0] = s;
+            }
+        }
+    }
+}
+
+// Widest tile (columns) whose slab fits; 0 if even the narrowest does not.
+template <typename BT>
+static int pick_cpt(int rows) {
+    const int max_cpt = sizeof(BT) == 4 ? 4 : 8;          // keeps pass-A shared-memory reads conflict-free
+    for (int cpt = max_cpt; cpt >= 1; cpt >>= 1)
+        if ((size_t)rows * kFusedConsumers * cpt * sizeof(BT) <= (size_t)kFusedSlabBytes) return cpt;
+    return 0;
+}
+
+template <typename BT, int CPT>
+static int launch_fused(const BT* V, int64_t ldv, int rows, const double* c_in, float* w, int64_t n, const Workspace& ws,
+                        double* c_out, double* norm2_out, cudaStream_t stream, const char* name) {
+    const size_t smem = fused_layout(rows, kFusedConsumers * CPT, (int)sizeof(BT)).total;
+    cudaError_t e = cudaFuncSetAttribute(cgs_update_project_kernel<BT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(update_project)");
+    const int64_t tw = kFusedConsumers * CPT;
+    const int grid = persistent_grid((n + tw - 1) / tw, 1);
+    cgs_update_project_kernel<BT, CPT><<<grid, kFusedThreads, smem, stream>>>(V, ldv, rows, c_in, w, n, ws.partials, ws.counters,
+                                                                              c_out, norm2_out);
+    HLV_LAUNCH_CHECK(name);
+    return HLV_OK;
+}
+
+template <typename BT>
+static int update_project(const char* name, const BT* V, int64_t ldv, int rows, const double* c_in, float* w, int64_t n,
+                          double* c_out, double* norm2_out, void* ws_raw, size_t ws_bytes, cudaStream_t stream) {
+    HLV_REQUIRE(V && w && c_in && c_out && norm2_out && n >= 0 && rows >= 1, HLV_ERR_ARG, "%s: bad argument", name);
+    HLV_REQUIRE(ldv >= n, HLV_ERR_ARG, "%s: ldv=%lld < n=%lld", name, (long long)ldv, (long long)n);
+    HLV_REQUIRE(aligned16(V) && aligned16(w) && ((ldv * (int64_t)sizeof(BT)) & 15) == 0, HLV_ERR_ALIGN,
+                "%s: V, w must be 16-byte aligned and ldv*sizeof(elem) a multiple of 16", name);
+    const int cpt = pick_cpt<BT>(rows);
+    HLV_REQUIRE(cpt > 0, HLV_ERR_ARG, "%s: rows=%d exceeds the fused kernel's shared-memory slab (max %d); use project+update",
+                name, rows, hlv_cgs_fused_max_rows((int)sizeof(BT)));
+    Workspace ws;
+    HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, rows + 1, &ws), HLV_ERR_WORKSPACE,
+                "%s: workspace too small for %d+1 rows (need %zu bytes)", name, rows, workspace_bytes(rows + 1));
+    HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "%s: no CUDA device", name);
+    switch (cpt) {
+        case 8:
+            if constexpr (sizeof(BT) == 2) return launch_fused<BT, 8>(V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
+        case 4: return launch_fused<BT, 4>(V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
+        case 2: return launch_fused<BT, 2>(V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
+        default: return launch_fused<BT, 1>(V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
+    }
+}
+
+}  // namespace hlv
+
+using namespace hlv;
+
+extern "C" {
+
+int hlv_cgs_fused_max_rows(int elem_bytes) {
+    if (elem_bytes != 2 && elem_bytes != 4) return 0;
+    return kFusedSlabBytes / (kFusedConsumers * elem_bytes);
+}
+
+int hlv_cgs_update_project_f32(const float* V, int64_t ldv, int rows, const double* c_in, float* w, int64_t n,
+                               double* c_out, double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return update_project<float>("hlv_cgs_update_project_f32", V, ldv, rows, c_in, w, n, c_out, norm2_out, ws, ws_bytes,
+                                 static_cast<cudaStream_t>(stream));
+}
+int hlv_cgs_update_project_bf16(const uint16_t* V, int64_t ldv, int rows, const double* c_in, float* w, int64_t n,
+                                double* c_out, double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return update_project<uint16_t>("hlv_cgs_update_project_bf16", V, ldv, rows, c_in, w, n, c_out, norm2_out, ws, ws_bytes,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -232,6 +232,10 @@ class GraphedHVP:
 
         def run():
             op.accumulate_into(self.v, self.out, dot_with=self.v, dot_out=self.dot, ws=self.ws, ops=kernels)
+        # A cached first-backward graph must be (re)built on the side stream: autograd replays each node on
+        # the stream its forward ran on, and a capture may fork into a side stream but never into the legacy
+        # default stream (cudaErrorStreamCaptureInvalidated).
+        op.clear_cache()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):

@@ -196,6 +196,27 @@ def cgs_update(V: torch.Tensor, rows: int, c: torch.Tensor, w: torch.Tensor,
     launch_count += 1
 
 
+def fused_max_rows(dtype: torch.dtype) -> int:
+    """Largest row count the fused update+project kernel can stage in shared memory."""
+    return int(_lib.load().hlv_cgs_fused_max_rows(4 if dtype == torch.float32 else 2))
+
+
+def cgs_update_project(V: torch.Tensor, rows: int, c_in: torch.Tensor, w: torch.Tensor, c_out: torch.Tensor,
+                       norm2_out: torch.Tensor, ws: Workspace) -> None:
+    """Middle pass of CGS2 in ONE read of the basis: w -= V^T c_in ; c_out = V w ; norm2_out = |w|^2
+    (TMA-staged shared-memory slab).  ws must have been created with max_rows >= rows + 1."""
+    global launch_count
+    n = w.numel()
+    p, ldv, sfx = _basis(V, rows, n, "cgs_update_project")
+    if c_out.numel() < rows:
+        raise ValueError("cgs_update_project: c_out too small")
+    with torch.cuda.device(w.device):
+        _lib.call(f"hlv_cgs_update_project_{sfx}", p, ldv, int(rows), _cuda(c_in, torch.float64, "c_in"),
+                  _cuda(w, torch.float32, "w"), n, _cuda(c_out, torch.float64, "c_out"),
+                  _cuda(norm2_out, torch.float64, "norm2_out"), ws.ptr, ws.nbytes, _stream())
+    launch_count += 1
+
+
 def vector_adjust(grad_vector: torch.Tensor, V: torch.Tensor, eigvals: torch.Tensor,
                   adjusted_grad_vector: torch.Tensor, delta: float, ws: Workspace,
                   coef_scratch: Optional[torch.Tensor] = None) -> torch.Tensor:

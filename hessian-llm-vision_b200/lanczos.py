@@ -78,12 +78,19 @@ class Comm:
 # CUDA-event phase timer (optional)
 # ----------------------------------------------------------------------------
 class _Phases:
+    """Per-phase CUDA-event timing (profile=True) and NVTX ranges (HLV_NVTX=1) around the kernels of an
+    iteration.  The reference only has wall-clock prints around each HVP (gpt2_savehessian.py:178-188)."""
+
     def __init__(self, enabled: bool):
+        import os
         self.enabled = enabled
+        self.nvtx = os.environ.get("HLV_NVTX", "0") == "1"
         self.pairs: List[Tuple[str, int, Any, Any]] = []
         self._open: Dict[str, Any] = {}
 
     def start(self, name: str) -> None:
+        if self.nvtx:
+            torch.cuda.nvtx.range_push(f"hlv:{name}")
         if self.enabled:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
@@ -94,6 +101,8 @@ class _Phases:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             self.pairs.append((name, rows, self._open.pop(name), e))
+        if self.nvtx:
+            torch.cuda.nvtx.range_pop()
 
     def summary(self) -> Dict[str, Dict[str, float]]:
         out: Dict[str, Dict[str, float]] = {}
@@ -174,7 +183,7 @@ class LanczosEngine:
     def __init__(self, hvp: Callable, n: int, n_iter: int, device, reorth: Optional[str] = None,
                  basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
                  breakdown_tol: Optional[float] = None, comm: Optional[Comm] = None, ops=None,
-                 profile: bool = False, column_vectors: bool = False, cgs_passes: int = 2):
+                 profile: bool = False, column_vectors: bool = False, cgs_passes: int = 2, fused_cgs: bool = True):
         if reorth not in (None, "full"):
             raise ValueError("reorth must be None or 'full'")
         if basis_dtype not in (torch.float32, torch.bfloat16):
@@ -222,8 +231,12 @@ class LanczosEngine:
         self.betas = torch.zeros(m + 1, **f64)          # betas[j+1] = ||w|| after iteration j; betas[0] unused
         self.norm2 = torch.zeros(1, **f64)
         self.coef = torch.zeros(max(m, 1), **f64)
+        self.coef2 = torch.zeros(max(m, 1), **f64)
         self.breakdown_iter = torch.full((1,), -1, dtype=torch.int32, device=self.device)
-        self.ws = ops.Workspace(self.device, max_rows=max(m, 1))
+        self.ws = ops.Workspace(self.device, max_rows=max(m, 1) + 1)
+        # fused middle pass of CGS2 (TMA-staged slab, basis read 3x instead of 4x per iteration)
+        self.fused = bool(fused_cgs) and self.keep_basis and hasattr(ops, "cgs_update_project")
+        self.fused_max_rows = ops.fused_max_rows(basis_dtype) if self.fused else 0
         self.j = 0
         self.launches = 0
 
@@ -326,14 +339,29 @@ class LanczosEngine:
         ph.stop("update")
         if self.reorth == "full":
             rows = j + 1
-            for _ in range(self.cgs_passes):
-                ph.start("cgs_project")
-                ops.cgs_project(self.basis, rows, self.w, self.coef, self.ws)
-                ph.stop("cgs_project", rows)
-                comm.all_reduce_sum(self.coef[:rows])
-                ph.start("cgs_update")
-                ops.cgs_update(self.basis, rows, self.coef, self.w, self.norm2, self.ws)
-                ph.stop("cgs_update", rows)
+            fused = self.fused and rows <= self.fused_max_rows
+            cur, nxt_c = self.coef, self.coef2
+            ph.start("cgs_project")
+            ops.cgs_project(self.basis, rows, self.w, cur, self.ws)
+            ph.stop("cgs_project", rows)
+            comm.all_reduce_sum(cur[:rows])
+            for p in range(self.cgs_passes - 1):
+                if fused:           # update with c_p and project for c_{p+1} in ONE pass over the basis
+                    ph.start("cgs_update_project")
+                    ops.cgs_update_project(self.basis, rows, cur, self.w, nxt_c, self.norm2, self.ws)
+                    ph.stop("cgs_update_project", rows)
+                else:
+                    ph.start("cgs_update")
+                    ops.cgs_update(self.basis, rows, cur, self.w, None, self.ws)
+                    ph.stop("cgs_update", rows)
+                    ph.start("cgs_project")
+                    ops.cgs_project(self.basis, rows, self.w, nxt_c, self.ws)
+                    ph.stop("cgs_project", rows)
+                comm.all_reduce_sum(nxt_c[:rows])
+                cur, nxt_c = nxt_c, cur
+            ph.start("cgs_update")
+            ops.cgs_update(self.basis, rows, cur, self.w, self.norm2, self.ws)
+            ph.stop("cgs_update", rows)
         comm.all_reduce_sum(self.norm2)
         if store_next:
             ph.start("normalize")
@@ -417,7 +445,7 @@ def lanczos(hvp: Callable, n_iter: int, v0: torch.Tensor, reorth: Optional[str] 
             basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
             breakdown_tol: Optional[float] = None, check_every: int = 16, normalize_v0: bool = False,
             comm: Optional[Comm] = None, ops=None, profile: bool = False, column_vectors: bool = False,
-            on_iteration: Optional[Callable[[int, LanczosEngine], None]] = None) -> LanczosResult:
+            on_iteration: Optional[Callable[[int, LanczosEngine], None]] = None, fused_cgs: bool = True) -> LanczosResult:
     """Run ``n_iter`` Lanczos iterations of the symmetric operator ``hvp`` from ``v0``.
 
     hvp: callable v[P] -> Hv.  It may return a flat [P] (or [P,1]) tensor, or -- to use the fused
@@ -433,7 +461,7 @@ def lanczos(hvp: Callable, n_iter: int, v0: torch.Tensor, reorth: Optional[str] 
         raise RuntimeError("lanczos: v0 must live on a CUDA device; this engine has no CPU path")
     eng = LanczosEngine(hvp, v0.numel(), n_iter, dev, reorth=reorth, basis_dtype=basis_dtype,
                         keep_basis=keep_basis, breakdown_tol=breakdown_tol, comm=comm, ops=ops,
-                        profile=profile, column_vectors=column_vectors)
+                        profile=profile, column_vectors=column_vectors, fused_cgs=fused_cgs)
     eng.start(v0, normalize=normalize_v0)
     for j in range(n_iter):
         eng.step(j)

@@ -73,5 +73,14 @@ def cgs_update(V, rows, c, w, norm2_out, ws, sign=-1.0):
         norm2_out[0] = torch.dot(w.double(), w.double())
 
 
+def fused_max_rows(dtype):
+    return 200 if dtype == torch.float32 else 400
+
+
+def cgs_update_project(V, rows, c_in, w, c_out, norm2_out, ws):
+    cgs_update(V, rows, c_in, w, norm2_out, ws)
+    cgs_project(V, rows, w, c_out, ws)
+
+
 def ritz_vectors(Q, m, Y, out, n):
     out[:, :n] = Y[:m].t() @ Q[:m, :n].float()

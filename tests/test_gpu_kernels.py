@@ -179,6 +179,55 @@ def test_cgs_project_update(K, cuda_dev, dtype, rows, n):
     assert float((w1 - w).abs().max()) <= 1e-5 * float(w.abs().max())
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,n", [(1, 1), (1, 300), (3, 2048), (8, 4096), (9, 2048 * 3 + 5), (26, 1_000_003), (50, 300_000),
+                                    (51, 300_000), (100, 65536 + 17), (100, 2_000_000), (101, 70_000), (200, 40_000)])
+def test_cgs_update_project_fused(K, cuda_dev, dtype, rows, n):
+    """Fused middle pass of CGS2 (TMA-staged slab): w' = w - V^T c ; c2 = V w' ; |w'|^2 in one read of V,
+    vs fp64 and vs the unfused update + project pair (same inputs)."""
+    V, w = _basis(rows, n, cuda_dev, dtype, rows * 11 + n)
+    ws = _ws(K, cuda_dev, rows + 1)
+    g = torch.Generator(device=cuda_dev).manual_seed(rows + n)
+    c = torch.randn(rows, dtype=torch.float64, device=cuda_dev, generator=g)
+    w1 = w.clone()
+    c2 = torch.full((rows,), float("nan"), dtype=torch.float64, device=cuda_dev)
+    nrm = torch.full((1,), float("nan"), dtype=torch.float64, device=cuda_dev)
+    K.cgs_update_project(V, rows, c, w1, c2, nrm, ws)
+    Vd = V[:, :n].double()
+    w_ref = w.double() - Vd.t() @ c.float().double()
+    assert float((w1.double() - w_ref).abs().max()) <= 1e-5 * float(w_ref.abs().max()) + 1e-12
+    assert abs(nrm.item() - float(w_ref @ w_ref)) <= 1e-5 * float(w_ref @ w_ref) + 1e-12
+    c2_ref = Vd @ w1.double()                                    # projection of the w' the kernel produced
+    tol = 3e-6 * float((Vd.abs() @ w1.double().abs()).max()) + 1e-12
+    assert float((c2 - c2_ref).abs().max()) <= tol
+    # unfused pair on the same inputs agrees
+    w2 = w.clone()
+    c2u = torch.zeros_like(c2)
+    nrm_u = torch.zeros_like(nrm)
+    K.cgs_update(V, rows, c, w2, nrm_u, ws)
+    K.cgs_project(V, rows, w2, c2u, ws)
+    assert float((w1 - w2).abs().max()) <= 2e-6 * float(w2.abs().max()) + 1e-12
+    assert float((c2 - c2u).abs().max()) <= 2 * tol
+    # deterministic
+    w3 = w.clone()
+    c3 = torch.zeros_like(c2)
+    K.cgs_update_project(V, rows, c, w3, c3, nrm, ws)
+    assert torch.equal(w3, w1) and torch.equal(c3, c2)
+
+
+def test_cgs_update_project_limits(K, cuda_dev):
+    from hessian_llm_vision_b200._lib import HLVError
+    assert K.fused_max_rows(torch.float32) == 200 and K.fused_max_rows(torch.bfloat16) == 400
+    V, w = _basis(201, 4096, cuda_dev, torch.float32, 1)
+    ws = _ws(K, cuda_dev, 202)
+    c = torch.zeros(201, dtype=torch.float64, device=cuda_dev)
+    with pytest.raises(HLVError, match="exceeds the fused kernel"):
+        K.cgs_update_project(V, 201, c, w, c.clone(), torch.zeros(1, dtype=torch.float64, device=cuda_dev), ws)
+    small = _ws(K, cuda_dev, 8)
+    with pytest.raises(HLVError, match="workspace too small"):
+        K.cgs_update_project(V, 8, c, w, c.clone(), torch.zeros(1, dtype=torch.float64, device=cuda_dev), small)
+
+
 def test_cgs2_orthogonalises_full_size(K, cuda_dev):
     """BASELINE full size (n = GPT-2's P), size-independent properties: after CGS2 against an
     orthonormal basis the result is orthogonal to every row, and the pass is idempotent."""
