@@ -137,8 +137,8 @@ __host__ __device__ inline FusedSmem fused_layout(int rows, int tw, int elem_byt
     L.slab = 0;
     L.s_w = (size_t)rows * tw * elem_bytes;
     L.s_c = L.s_w + (size_t)tw * 4;
-    L.s_acc = L.s_c + (size_t)((rows + 3) / 4 * 4) * 4;
-    L.bars = L.s_acc + (size_t)rows * 8;
+    L.s_acc = L.s_c + (size_t)ngroups * kGroup * 4;        // c and the accumulators are padded to whole groups
+    L.bars = L.s_acc + (size_t)ngroups * kGroup * 8;
     L.total = L.bars + (size_t)ngroups * 16;
     return L;
 }
@@ -165,13 +165,14 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
     if (tid == 0) {
         for (int g = 0; g < ngroups; ++g) {
             const int rows_g = min(kGroup, rows - g * kGroup);
-            mbar_init(&full[g], 1);
-            mbar_init(&empty[g], rows_g);
+            (void)rows_g;
+            mbar_init(&full[g], 1);                  // the producer's arrive.expect_tx (+ the bytes of the group's rows)
+            mbar_init(&empty[g], 1);                 // the owning consumer warp's release after pass B
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < rows; i += kFusedThreads) {
-        s_c[i] = -(float)c_in[i];
+    for (int i = tid; i < ngroups * kGroup; i += kFusedThreads) {
+        s_c[i] = i < rows ? -(float)c_in[i] : 0.0f;
         s_acc[i] = 0.0;
     }
     __syncthreads();
@@ -228,16 +229,19 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
                 if (!manual) mbar_wait(&full[g], it & 1u);
                 const int i0 = g * kGroup;
                 const int rows_g = min(kGroup, rows - i0);
+                const float4 ca = *reinterpret_cast<const float4*>(s_c + i0);       // 8 coefficients, 2 broadcasts
+                const float4 cb = *reinterpret_cast<const float4*>(s_c + i0 + 4);
+                const float cg[kGroup] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                float v[kGroup][CPT];
 #pragma unroll
-                for (int r = 0; r < kGroup; ++r) {
+                for (int r = 0; r < kGroup; ++r)                                      // all loads first ...
+                    if (r < rows_g) SlabVec<BT, CPT>::load(slab + (size_t)(i0 + r) * TW + tid * CPT, v[r]);
+#pragma unroll
+                for (int r = 0; r < kGroup; ++r)                                      // ... then the FMAs
                     if (r < rows_g) {
-                        const float ci = s_c[i0 + r];
-                        float v[CPT];
-                        SlabVec<BT, CPT>::load(slab + (size_t)(i0 + r) * TW + tid * CPT, v);
 #pragma unroll
-                        for (int q = 0; q < CPT; ++q) acc[q] = fmaf(ci, v[q], acc[q]);
+                        for (int q = 0; q < CPT; ++q) acc[q] = fmaf(cg[r], v[r][q], acc[q]);
                     }
-                }
             }
             consumer_bar();                                        // nobody still reads s_w from the previous pass B
             if (!manual) {
@@ -251,26 +255,45 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
 #pragma unroll
             for (int q = 0; q < CPT; ++q) nrm = fmaf(acc[q], acc[q], nrm);
             consumer_bar();                                        // w' tile complete in shared memory
-            // ---- pass B: c2[i] += <V[i, tile], w'>, warp (i mod 8) owns row i ----
-            constexpr int E = Chunk16<BT>::kElems;
-            for (int i = warp; i < rows; i += kWarps) {
-                const BT* row = slab + (size_t)i * TW;
-                float p = 0.0f;
-                for (int x = lane * E; x < TW; x += 32 * E) {
-                    float v[8];
-                    Chunk16<BT>::load(row + x, v);
-                    const float4 a = *reinterpret_cast<const float4*>(s_w + x);
-                    p = fmaf(v[0], a.x, p); p = fmaf(v[1], a.y, p); p = fmaf(v[2], a.z, p); p = fmaf(v[3], a.w, p);
-                    if (E == 8) {
-                        const float4 b = *reinterpret_cast<const float4*>(s_w + x + 4);
-                        p = fmaf(v[4], b.x, p); p = fmaf(v[5], b.y, p); p = fmaf(v[6], b.z, p); p = fmaf(v[7], b.w, p);
+            // ---- pass B: c2[i] += <V[i, tile], w'>.  Warp (g mod 8) owns row group g: its lanes keep their
+            //      columns of w' in registers, run 8 independent row accumulators, and reduce all 8 rows with
+            //      ONE 9-shuffle butterfly; then the group's slots go back to the producer. ----
+            constexpr int E = Chunk16<BT>::kElems;                  // elements per 16-byte chunk
+            constexpr int NCH = TW / (32 * E);                      // chunks per lane per row
+            float wr[NCH][E];
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const float* src = s_w + (k * 32 + lane) * E;
+                const float4 a = *reinterpret_cast<const float4*>(src);
+                wr[k][0] = a.x; wr[k][1] = a.y; wr[k][2] = a.z; wr[k][3] = a.w;
+                if (E == 8) {
+                    const float4 b = *reinterpret_cast<const float4*>(src + 4);
+                    wr[k][4 % E] = b.x; wr[k][5 % E] = b.y; wr[k][6 % E] = b.z; wr[k][7 % E] = b.w;
+                }
+            }
+            const int my_row = warp_sum8_row(lane);
+            for (int g = warp; g < ngroups; g += kWarps) {
+                const int i0 = g * kGroup;
+                const int rows_g = min(kGroup, rows - i0);
+                float p[kGroup];
+#pragma unroll
+                for (int r = 0; r < kGroup; ++r) {
+                    p[r] = 0.0f;
+                    if (r < rows_g) {
+                        const BT* row = slab + (size_t)(i0 + r) * TW;
+#pragma unroll
+                        for (int k = 0; k < NCH; ++k) {
+                            float v[8];
+                            Chunk16<BT>::load(row + (k * 32 + lane) * E, v);
+#pragma unroll
+                            for (int e = 0; e < E; ++e) p[r] = fmaf(v[e], wr[k][e], p[r]);
+                        }
                     }
                 }
-                p = warp_sum(p);
-                if (lane == 0) {
-                    s_acc[i] += (double)p;
-                    if (!manual) mbar_arrive(&empty[i / kGroup]);  // hand the row's slot back to the producer
-                }
+                const float tot = warp_sum8(p, lane);
+                if ((lane & 3) == 0 && my_row < rows_g) s_acc[i0 + my_row] += (double)tot;
+                __syncwarp();                                       // every lane is done reading the group's rows
+                if (lane == 0 && !manual) mbar_arrive(&empty[g]);   // hand the group's slots back to the producer
             }
         }
     }
