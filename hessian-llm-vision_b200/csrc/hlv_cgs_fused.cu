@@ -21,7 +21,10 @@ namespace hlv {
 constexpr int kFusedConsumers = 256;
 constexpr int kFusedThreads = kFusedConsumers + 32;      // + one producer warp
 constexpr int kGroup = 8;                                // rows per mbarrier
-constexpr int kFusedSlabBytes = 200 * 1024;
+// Two CTAs per SM, each with a <= 100 KB slab: while one CTA waits for its tile to land, the other is in its
+// compute passes, so HBM stays busy (a single 200 KB slab cannot overlap a tile's load with its own compute).
+constexpr int kFusedCtasPerSm = 2;
+constexpr int kFusedSlabBytes = 100 * 1024;
 
 // ---- mbarrier / TMA (1-D bulk) PTX ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,8 +146,18 @@ __host__ __device__ inline FusedSmem fused_layout(int rows, int tw, int elem_byt
     return L;
 }
 
+template <typename Kernel>
+static int resident_ctas_fused(Kernel kernel, size_t smem) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFusedThreads, smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 1;
+    }
+    return per_sm;
+}
+
 template <typename BT, int CPT>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+__global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm)
 cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const double* __restrict__ c_in,
                           float* __restrict__ w, int64_t n, double* partials, unsigned* counter,
                           double* c_out, double* norm2_out) {
@@ -182,19 +195,21 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
     float nrm = 0.0f;
 
     if (warp == kWarps) {
-        // ===== producer: one elected lane streams row tiles into the slab =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles_full; tile += gridDim.x, ++it) {
-                const BT* col0 = V + tile * TW;
-                for (int g = 0; g < ngroups; ++g) {
-                    const int rows_g = min(kGroup, rows - g * kGroup);
+        // ===== producer warp: every lane issues one row copy per step (4 row groups in flight per step) =====
+        // lane l serves row (l & 7) of group 4*q + (l >> 3).  The expect_tx may reach the barrier after some
+        // of the group's bytes have landed (the tx-count goes transiently negative, which PTX allows): the
+        // phase cannot complete before the single pending arrival -- the expect_tx itself -- has happened.
+        uint32_t it = 0;
+        const int r = lane & 7;
+        for (int64_t tile = blockIdx.x; tile < ntiles_full; tile += gridDim.x, ++it) {
+            const BT* col0 = V + tile * TW;
+            for (int g = lane >> 3; g < ngroups; g += 4) {
+                const int rows_g = min(kGroup, rows - g * kGroup);
+                if (r < rows_g) {
                     mbar_wait(&empty[g], (it & 1u) ^ 1u);          // slot group free (passes at once on the first tile)
-                    mbar_arrive_expect_tx(&full[g], (uint32_t)(rows_g * TW * sizeof(BT)));
-                    for (int r = 0; r < rows_g; ++r) {
-                        const int i = g * kGroup + r;
-                        tma_bulk_g2s(slab + (size_t)i * TW, col0 + (int64_t)i * ldv, (uint32_t)(TW * sizeof(BT)), &full[g]);
-                    }
+                    if (r == 0) mbar_arrive_expect_tx(&full[g], (uint32_t)(rows_g * TW * sizeof(BT)));
+                    const int i = g * kGroup + r;
+                    tma_bulk_g2s(slab + (size_t)i * TW, col0 + (int64_t)i * ldv, (uint32_t)(TW * sizeof(BT)), &full[g]);
                 }
             }
         }
@@ -344,7 +359,7 @@ static int launch_fused(const BT* V, int64_t ldv, int rows, const double* c_in, 
     cudaError_t e = cudaFuncSetAttribute(cgs_update_project_kernel<BT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(update_project)");
     const int64_t tw = kFusedConsumers * CPT;
-    const int grid = persistent_grid((n + tw - 1) / tw, 1);
+    const int grid = persistent_grid((n + tw - 1) / tw, resident_ctas_fused(cgs_update_project_kernel<BT, CPT>, smem));
     cgs_update_project_kernel<BT, CPT><<<grid, kFusedThreads, smem, stream>>>(V, ldv, rows, c_in, w, n, ws.partials, ws.counters,
                                                                               c_out, norm2_out);
     HLV_LAUNCH_CHECK(name);
