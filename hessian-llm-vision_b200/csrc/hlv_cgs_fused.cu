@@ -4,16 +4,19 @@
 // Two-pass classical Gram-Schmidt is project, update, project, update = 4 streaming passes over the
 // basis.  The 2nd and 3rd touch the same data in the same order, and the 3rd needs nothing global from
 // the 2nd (w' is complete per column as soon as all rows of that column have been applied).  On B200 a
-// CTA can hold a whole [rows x TW] column slab of the basis in its 227 KB of shared memory (100 fp32 rows
-// x 512 columns = 200 KB), so: apply the update from the slab as its rows land (pass A), then project the
-// finished w' tile against the SAME slab (pass B).  CGS2 becomes 3 passes: (3*j*s + 20)*n bytes
-// instead of (4*j*s + 24)*n.
+// CTA can hold a whole [rows x TW] column slab of the basis in shared memory (100 fp32 rows x 256 columns
+// = 100 KB; two such CTAs per SM), so: apply the update from the slab as its rows land (pass A), then
+// project the finished w' tile against the SAME slab (pass B).  CGS2 becomes 3 passes:
+// (3*j*s + 20)*n bytes instead of (4*j*s + 24)*n.
 //
-// Data movement is TMA: one elected producer thread issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP)
-// row by row into the slab; completion is tracked by mbarriers (one per group of 8 rows so a consumer
-// pays one try_wait per 8 rows), and each row's slot is handed back to the producer the moment pass B
-// has consumed it, so the next tile's loads are in flight while this tile is still being projected.
-// 8 consumer warps: pass A "thread owns columns", pass B "warp owns rows" (fixed-order reductions).
+// Data movement is TMA: the producer warp issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP), one row per
+// lane, into the slab; completion is tracked by mbarriers (one per group of 8 rows so a consumer pays one
+// try_wait per 8 rows), and a group's slots are handed back to the producer the moment pass B has consumed
+// them, so the next tile's loads are in flight while this tile is still being projected.
+// 8 consumer warps: pass A "thread owns columns", pass B "warp owns row groups" (fixed-order reductions).
+// Measured (profiles/): 1.3-1.9x faster than the project+update pair it replaces for fp32 rows (6.6 TB/s at
+// rows=25, 4.7 TB/s at rows=100 where the tile is only 256 columns wide and the passes become issue-bound);
+// not a win for bf16 rows (twice the FMAs per byte), where the engine keeps the unfused pair.
 #include "hlv_common.cuh"
 
 namespace hlv {

@@ -235,8 +235,12 @@ class LanczosEngine:
         self.breakdown_iter = torch.full((1,), -1, dtype=torch.int32, device=self.device)
         self.ws = ops.Workspace(self.device, max_rows=max(m, 1) + 1)
         # fused middle pass of CGS2 (TMA-staged slab, basis read 3x instead of 4x per iteration)
-        self.fused = bool(fused_cgs) and self.keep_basis and hasattr(ops, "cgs_update_project")
+        # Measured policy (profiles/r01_cgs_kernels.json): a win for fp32 rows from ~8 rows up; bf16 rows carry
+        # twice the FMAs per byte and the unfused pair is faster there.  fused_cgs="force" overrides.
+        want = fused_cgs == "force" or (bool(fused_cgs) and basis_dtype == torch.float32)
+        self.fused = want and self.keep_basis and hasattr(ops, "cgs_update_project")
         self.fused_max_rows = ops.fused_max_rows(basis_dtype) if self.fused else 0
+        self.fused_min_rows = 1 if fused_cgs == "force" else 8
         self.j = 0
         self.launches = 0
 
@@ -339,7 +343,7 @@ class LanczosEngine:
         ph.stop("update")
         if self.reorth == "full":
             rows = j + 1
-            fused = self.fused and rows <= self.fused_max_rows
+            fused = self.fused and self.fused_min_rows <= rows <= self.fused_max_rows
             cur, nxt_c = self.coef, self.coef2
             ph.start("cgs_project")
             ops.cgs_project(self.basis, rows, self.w, cur, self.ws)

@@ -120,6 +120,25 @@ def test_full_reorth_vs_oracle(hlv, cuda_dev, n, m):
     assert abs(float((res.eigvals * res.gammas).sum()) - float(res.alphas[0])) < 1e-4 * scale
 
 
+def test_fused_and_unfused_cgs2_agree(hlv, cuda_dev):
+    """CGS2 as 3 passes (fused TMA-slab middle pass) and as 4 separate passes is the same arithmetic per
+    element; only the reduction trees of the second projection differ."""
+    torch.manual_seed(12)
+    n, m = 70_003, 60
+    d = (torch.randn(n) * 2).to(cuda_dev)
+    v0 = hlv.probe_vector(n, 3, cuda_dev)
+    op = lambda q: d * q
+    a = hlv.lanczos(op, m, v0, reorth="full", fused_cgs=True)
+    b = hlv.lanczos(op, m, v0, reorth="full", fused_cgs=False)
+    scale = float(b.T.abs().max())
+    assert _rel(a.T, b.T, scale) < 2e-6
+    Q = a.Q.double()
+    assert float((Q @ Q.t() - torch.eye(m, dtype=torch.float64, device=cuda_dev)).abs().max()) < 5e-6
+    c = hlv.lanczos(op, 20, v0, reorth="full", basis_dtype=torch.bfloat16, fused_cgs="force")
+    e = hlv.lanczos(op, 20, v0, reorth="full", basis_dtype=torch.bfloat16, fused_cgs=False)
+    assert _rel(c.T, e.T, scale) < 1e-4
+
+
 def test_bf16_basis_vs_bf16_oracle(hlv, cuda_dev):
     M, v0 = _sym(9, 2000)
     Md = M.to(cuda_dev)
