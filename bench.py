@@ -380,7 +380,7 @@ def run_ours(args, rank, world, local_rank):
         roofline = {"bound": "hbm", "kernel": kname, "achieved": kernels_out[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels_out[top]["frac_of_peak"], "bytes_per_launch": kernels_out[top]["bytes_per_launch"],
                     "traffic": ncu_traffic(top, kernels_out[top]["bytes_per_launch"]), "peak_source": peak_src,
-                    "bytes_model": "project: (rows*s+4)*n per launch; update: (rows*s+8)*n per launch (DESIGN.md)",
+                    "bytes_model": "project: (rows*s+4)*n; update and fused update_project: (rows*s+8)*n per launch (DESIGN.md section 3)",
                     "share_of_step": round(kernels_out[top]["ms_total"] / ms, 4)}
     line = {"metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

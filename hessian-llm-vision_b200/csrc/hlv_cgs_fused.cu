@@ -17,6 +17,8 @@
 // Measured (profiles/): 1.3-1.9x faster than the project+update pair it replaces for fp32 rows (6.6 TB/s at
 // rows=25, 4.7 TB/s at rows=100 where the tile is only 256 columns wide and the passes become issue-bound);
 // not a win for bf16 rows (twice the FMAs per byte), where the engine keeps the unfused pair.
+#include <stdlib.h>
+
 #include "hlv_common.cuh"
 
 namespace hlv {
@@ -347,11 +349,23 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
 }
 
 // Widest tile (columns) whose slab fits; 0 if even the narrowest does not.
+// Slab budget per CTA.  Default 100 KB = two CTAs per SM; HLV_FUSED_SLAB_KB (tuning knob, read once) can raise
+// it to ~200 KB = one CTA per SM with a tile twice as wide.
+static size_t slab_budget() {
+    static size_t budget = 0;
+    if (budget == 0) {
+        const char* e = getenv("HLV_FUSED_SLAB_KB");
+        long kb = e ? atol(e) : 0;
+        budget = (kb >= 16 && kb <= 208) ? (size_t)kb * 1024 : (size_t)kFusedSlabBytes;
+    }
+    return budget;
+}
+
 template <typename BT>
 static int pick_cpt(int rows) {
     const int max_cpt = sizeof(BT) == 4 ? 4 : 8;          // keeps pass-A shared-memory reads conflict-free
     for (int cpt = max_cpt; cpt >= 1; cpt >>= 1)
-        if ((size_t)rows * kFusedConsumers * cpt * sizeof(BT) <= (size_t)kFusedSlabBytes) return cpt;
+        if ((size_t)rows * kFusedConsumers * cpt * sizeof(BT) <= slab_budget()) return cpt;
     return 0;
 }
 
@@ -400,7 +414,7 @@ extern "C" {
 
 int hlv_cgs_fused_max_rows(int elem_bytes) {
     if (elem_bytes != 2 && elem_bytes != 4) return 0;
-    return kFusedSlabBytes / (kFusedConsumers * elem_bytes);
+    return (int)(slab_budget() / (size_t)(kFusedConsumers * elem_bytes));
 }
 
 int hlv_cgs_update_project_f32(const float* V, int64_t ldv, int rows, const double* c_in, float* w, int64_t n,

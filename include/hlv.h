@@ -121,8 +121,8 @@ int hlv_cgs_update_bf16(const uint16_t* V, int64_t ldv, int rows, const double* 
 /* Fused middle pass of two-pass Gram-Schmidt: w -= V^T c_in ; c_out = V w_new ; norm2_out = |w_new|^2,
  * reading V from HBM once (a [rows x tile] slab is staged in shared memory by TMA bulk copies and used
  * for both the update and the projection).  CGS2 = project, update_project, update: 3 passes over V
- * instead of 4.  rows <= hlv_cgs_fused_max_rows(sizeof(elem)) (200 fp32 / 400 bf16); ws must hold
- * rows+1 partial rows: hlv_workspace_bytes(rows + 1). */
+ * instead of 4.  rows <= hlv_cgs_fused_max_rows(sizeof(elem)) (100 fp32 / 200 bf16: two 100 KB slabs
+ * per SM); ws must hold rows+1 partial rows: hlv_workspace_bytes(rows + 1). */
 int hlv_cgs_fused_max_rows(int elem_bytes);
 int hlv_cgs_update_project_f32 (const float*    V, int64_t ldv, int rows, const double* c_in,
                                 float* w, int64_t n, double* c_out, double* norm2_out,
