@@ -137,14 +137,19 @@ template <int CPT> __device__ __forceinline__ void st_f32(float* p, const float 
 }
 
 struct FusedSmem {
-    size_t slab, s_w, s_c, s_acc, bars, total;
+    size_t slab, s_w, s_part, s_c, s_acc, bars, total;
 };
+// Pass A works on 16-byte chunks: a row of the tile is tw*elem_bytes/16 chunks, shared by 256 threads as
+// `slices` = 256 / chunks row slices (1 for the widest tile, 4 for the 256-column fp32 tile).
+__host__ __device__ inline int fused_slices(int tw, int elem_bytes) { return kFusedConsumers / (tw * elem_bytes / 16); }
 __host__ __device__ inline FusedSmem fused_layout(int rows, int tw, int elem_bytes) {
     FusedSmem L;
     const int ngroups = (rows + kGroup - 1) / kGroup;
+    const int slices = fused_slices(tw, elem_bytes);
     L.slab = 0;
     L.s_w = (size_t)rows * tw * elem_bytes;
-    L.s_c = L.s_w + (size_t)tw * 4;
+    L.s_part = L.s_w + (size_t)tw * 4;                       // [slices][tw] partial updates (only when slices > 1)
+    L.s_c = L.s_part + (slices > 1 ? (size_t)slices * tw * 4 : 0);
     L.s_acc = L.s_c + (size_t)ngroups * kGroup * 4;        // c and the accumulators are padded to whole groups
     L.bars = L.s_acc + (size_t)ngroups * kGroup * 8;
     L.total = L.bars + (size_t)ngroups * 16;
@@ -171,6 +176,7 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
     const FusedSmem L = fused_layout(rows, TW, (int)sizeof(BT));
     BT* slab = reinterpret_cast<BT*>(smem + L.slab);
     float* s_w = reinterpret_cast<float*>(smem + L.s_w);
+    float* s_part = reinterpret_cast<float*>(smem + L.s_part);
     float* s_c = reinterpret_cast<float*>(smem + L.s_c);
     double* s_acc = reinterpret_cast<double*>(smem + L.s_acc);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -220,19 +226,28 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
         }
     } else {
         // ===== consumers =====
+        // Pass A mapping: a thread always works on one 16-byte chunk of a row (E elements, one LDS.128 per E
+        // FMAs).  A tile row has NQ chunks; when the tile is narrow (NQ < 256) the 256 threads split the row
+        // groups into S = 256/NQ slices (slice s takes groups s, s+S, ...), and the S partial updates are
+        // summed in slice order through shared memory -- same instruction count per byte for every width.
+        constexpr int E = Chunk16<BT>::kElems;                  // elements per 16-byte chunk
+        constexpr int NQ = TW / E;                              // chunks per tile row
+        constexpr int S = kFusedConsumers / NQ;                 // row slices
+        static_assert(NQ * S == kFusedConsumers && (S > 1 || E == CPT), "tile width / slice mapping");
+        const int q = tid % NQ, slice = tid / NQ;
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const bool manual = tile >= ntiles_full;               // ragged last tile: filled by hand, zero padded
             const int64_t x0 = tile * TW;
             const int valid = (int)((n - x0 < TW) ? (n - x0) : TW);
-            float acc[CPT];
-            if (!manual) {
-                ld_f32<CPT>(w + x0 + tid * CPT, acc);
+            float acc[E];
+            if (slice == 0 && !manual) {
+                ld_f32<E>(w + x0 + q * E, acc);
             } else {
 #pragma unroll
-                for (int q = 0; q < CPT; ++q) {
-                    const int x = tid * CPT + q;
-                    acc[q] = x < valid ? w[x0 + x] : 0.0f;
+                for (int e = 0; e < E; ++e) {
+                    const int x = q * E + e;
+                    acc[e] = (slice == 0 && x < valid) ? w[x0 + x] : 0.0f;
                 }
             }
             if (manual) {
@@ -245,40 +260,71 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
                 consumer_bar();
             }
             // ---- pass A: w' = w - sum_i c1[i] V[i, tile] ----
-            for (int g = 0; g < ngroups; ++g) {
+            for (int g = slice; g < ngroups; g += S) {
                 if (!manual) mbar_wait(&full[g], it & 1u);
                 const int i0 = g * kGroup;
                 const int rows_g = min(kGroup, rows - i0);
                 const float4 ca = *reinterpret_cast<const float4*>(s_c + i0);       // 8 coefficients, 2 broadcasts
                 const float4 cb = *reinterpret_cast<const float4*>(s_c + i0 + 4);
                 const float cg[kGroup] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                float v[kGroup][CPT];
+                const BT* col = slab + (size_t)i0 * TW + q * E;
+                if (rows_g == kGroup) {
+                    float v[kGroup][8];
 #pragma unroll
-                for (int r = 0; r < kGroup; ++r)                                      // all loads first ...
-                    if (r < rows_g) SlabVec<BT, CPT>::load(slab + (size_t)(i0 + r) * TW + tid * CPT, v[r]);
+                    for (int r = 0; r < kGroup; ++r) Chunk16<BT>::load(col + r * TW, v[r]);   // all loads first ...
 #pragma unroll
-                for (int r = 0; r < kGroup; ++r)                                      // ... then the FMAs
-                    if (r < rows_g) {
+                    for (int r = 0; r < kGroup; ++r) {                                        // ... then the FMAs
 #pragma unroll
-                        for (int q = 0; q < CPT; ++q) acc[q] = fmaf(cg[r], v[r][q], acc[q]);
+                        for (int e = 0; e < E; ++e) acc[e] = fmaf(cg[r], v[r][e], acc[e]);
                     }
+                } else {
+                    for (int r = 0; r < rows_g; ++r) {
+                        float v[8];
+                        Chunk16<BT>::load(col + r * TW, v);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) acc[e] = fmaf(s_c[i0 + r], v[e], acc[e]);
+                    }
+                }
             }
-            consumer_bar();                                        // nobody still reads s_w from the previous pass B
-            if (!manual) {
-                st_f32<CPT>(w + x0 + tid * CPT, acc);
+            if constexpr (S == 1) {
+                consumer_bar();                                    // nobody still reads s_w from the previous pass B
+                if (!manual) {
+                    st_f32<E>(w + x0 + q * E, acc);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        if (q * E + e < valid) w[x0 + q * E + e] = acc[e];
+                }
+                st_f32<E>(s_w + q * E, acc);                       // columns >= valid hold 0
+#pragma unroll
+                for (int e = 0; e < E; ++e) nrm = fmaf(acc[e], acc[e], nrm);
             } else {
+                st_f32<E>(s_part + slice * TW + q * E, acc);
+                consumer_bar();                                    // partials visible; previous pass B is over too
+                float fin[CPT];
+                ld_f32<CPT>(s_part + tid * CPT, fin);
 #pragma unroll
-                for (int q = 0; q < CPT; ++q)
-                    if (tid * CPT + q < valid) w[x0 + tid * CPT + q] = acc[q];
+                for (int sl = 1; sl < S; ++sl) {                   // fixed slice order
+                    float t[CPT];
+                    ld_f32<CPT>(s_part + sl * TW + tid * CPT, t);
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) fin[c] += t[c];
+                }
+                if (!manual) {
+                    st_f32<CPT>(w + x0 + tid * CPT, fin);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c)
+                        if (tid * CPT + c < valid) w[x0 + tid * CPT + c] = fin[c];
+                }
+                st_f32<CPT>(s_w + tid * CPT, fin);                 // columns >= valid hold 0
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) nrm = fmaf(fin[c], fin[c], nrm);
             }
-            st_f32<CPT>(s_w + tid * CPT, acc);                     // columns >= valid hold 0
-#pragma unroll
-            for (int q = 0; q < CPT; ++q) nrm = fmaf(acc[q], acc[q], nrm);
             consumer_bar();                                        // w' tile complete in shared memory
             // ---- pass B: c2[i] += <V[i, tile], w'>.  Warp (g mod 8) owns row group g: its lanes keep their
             //      columns of w' in registers, run 8 independent row accumulators, and reduce all 8 rows with
             //      ONE 9-shuffle butterfly; then the group's slots go back to the producer. ----
-            constexpr int E = Chunk16<BT>::kElems;                  // elements per 16-byte chunk
             constexpr int NCH = TW / (32 * E);                      // chunks per lane per row
             float wr[NCH][E];
 #pragma unroll
