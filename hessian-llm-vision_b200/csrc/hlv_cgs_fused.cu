@@ -4,19 +4,22 @@
 // Two-pass classical Gram-Schmidt is project, update, project, update = 4 streaming passes over the
 // basis.  The 2nd and 3rd touch the same data in the same order, and the 3rd needs nothing global from
 // the 2nd (w' is complete per column as soon as all rows of that column have been applied).  On B200 a
-// CTA can hold a whole [rows x TW] column slab of the basis in shared memory (100 fp32 rows x 256 columns
-// = 100 KB; two such CTAs per SM), so: apply the update from the slab as its rows land (pass A), then
+// CTA can hold a whole [rows x TW] column slab of the basis in shared memory (104 fp32 rows x 256 columns
+// = 104 KB; two such CTAs per SM), so: apply the update from the slab as its rows land (pass A), then
 // project the finished w' tile against the SAME slab (pass B).  CGS2 becomes 3 passes:
 // (3*j*s + 20)*n bytes instead of (4*j*s + 24)*n.
 //
-// Data movement is TMA: the producer warp issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP), one row per
-// lane, into the slab; completion is tracked by mbarriers (one per group of 8 rows so a consumer pays one
-// try_wait per 8 rows), and a group's slots are handed back to the producer the moment pass B has consumed
-// them, so the next tile's loads are in flight while this tile is still being projected.
-// 8 consumer warps: pass A "thread owns columns", pass B "warp owns row groups" (fixed-order reductions).
-// Measured (profiles/): 1.3-1.9x faster than the project+update pair it replaces for fp32 rows (6.6 TB/s at
-// rows=25, 4.7 TB/s at rows=100 where the tile is only 256 columns wide and the passes become issue-bound);
-// not a win for bf16 rows (twice the FMAs per byte), where the engine keeps the unfused pair.
+// Data movement is 2-D tiled TMA (cp.async.bulk.tensor.2d, SASS UTMALDG): the basis is described to the
+// TMA unit as a [rows x n] tensor with row pitch ldv, and the producer warp asks for one [8 rows x 256
+// columns] box per instruction -- 8 KB per request.  (The first version issued one 1-D bulk copy per row;
+// at 256-column tiles that is a 1 KB request every ~50 cycles per SM, and the request rate, not HBM,
+// bounded the kernel at 4.9 TB/s.)  Rows past `rows` and columns past n are out of bounds for the tensor
+// map and arrive as zeros, so neither the last row group nor the ragged last tile needs special code.
+// Completion is tracked by one mbarrier per 8-row group; a group's slots are handed back to the producer
+// the moment pass B has consumed them, so the next tile's boxes are in flight while this tile is still
+// being projected.  8 consumer warps: pass A "thread owns a 16-byte chunk of a row slice", pass B "warp
+// owns row groups" (fixed-order reductions).
+#include <cuda.h>        // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through the runtime
 #include <stdlib.h>
 
 #include "hlv_common.cuh"
@@ -25,18 +28,20 @@ namespace hlv {
 
 constexpr int kFusedConsumers = 256;
 constexpr int kFusedThreads = kFusedConsumers + 32;      // + one producer warp
-constexpr int kGroup = 8;                                // rows per mbarrier
-// Two CTAs per SM, each with a <= 100 KB slab: while one CTA waits for its tile to land, the other is in its
-// compute passes, so HBM stays busy (a single 200 KB slab cannot overlap a tile's load with its own compute).
+constexpr int kGroup = 8;                                // rows per mbarrier = rows per TMA box
+constexpr int kBoxCols = 256;                            // columns per TMA box (the hardware maximum per dimension)
+// Two CTAs per SM, each with a <= 104 KB slab: while one CTA waits for its tile to land, the other is in its
+// compute passes, so HBM stays busy (a single 208 KB slab cannot overlap a tile's load with its own compute).
 constexpr int kFusedCtasPerSm = 2;
-constexpr int kFusedSlabBytes = 100 * 1024;
+constexpr int kFusedSlabBytes = 104 * 1024;
 
-// ---- mbarrier / TMA (1-D bulk) PTX ---------------------------------------------------------------
+// ---- mbarrier / TMA PTX ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -54,15 +59,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// one [kGroup x kBoxCols] box of the tensor at column x, row y -> shared memory, completing on `bar`
+__device__ __forceinline__ void tma_box_g2s(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kFusedConsumers) : "memory"); }
-
-template <typename BT> __device__ __forceinline__ float elem_to_float(BT x);
-template <> __device__ __forceinline__ float elem_to_float<float>(float x) { return x; }
-template <> __device__ __forceinline__ float elem_to_float<uint16_t>(uint16_t x) { return __uint_as_float((uint32_t)x << 16); }
 
 // 16 bytes of a slab row -> floats (4 fp32 or 8 bf16)
 template <typename BT> struct Chunk16;
@@ -82,42 +84,6 @@ template <> struct Chunk16<uint16_t> {
     }
 };
 
-// CPT consecutive slab elements of one thread -> floats, as ONE shared-memory access (conflict-free:
-// consecutive lanes read consecutive 4/8/16-byte words).
-template <typename BT, int CPT> struct SlabVec {
-    static __device__ __forceinline__ void load(const BT* p, float (&v)[CPT]) {
-#pragma unroll
-        for (int q = 0; q < CPT; ++q) v[q] = elem_to_float<BT>(p[q]);
-    }
-};
-template <> struct SlabVec<float, 2> {
-    static __device__ __forceinline__ void load(const float* p, float (&v)[2]) {
-        float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
-    }
-};
-template <> struct SlabVec<float, 4> {
-    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
-        float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-};
-template <> struct SlabVec<uint16_t, 2> {
-    static __device__ __forceinline__ void load(const uint16_t* p, float (&v)[2]) {
-        uint32_t u = *reinterpret_cast<const uint32_t*>(p); v[0] = bf16_lo(u); v[1] = bf16_hi(u);
-    }
-};
-template <> struct SlabVec<uint16_t, 4> {
-    static __device__ __forceinline__ void load(const uint16_t* p, float (&v)[4]) {
-        uint2 u = *reinterpret_cast<const uint2*>(p);
-        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
-    }
-};
-template <> struct SlabVec<uint16_t, 8> {
-    static __device__ __forceinline__ void load(const uint16_t* p, float (&v)[8]) {
-        uint4 u = *reinterpret_cast<const uint4*>(p);
-        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
-        v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
-    }
-};
 // CPT consecutive floats of w / s_w as one access when the tile is full
 template <int CPT> __device__ __forceinline__ void ld_f32(const float* p, float (&v)[CPT]) {
     if (CPT == 2) { float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1 % CPT] = t.y; }
@@ -142,12 +108,13 @@ struct FusedSmem {
 // Pass A works on 16-byte chunks: a row of the tile is tw*elem_bytes/16 chunks, shared by 256 threads as
 // `slices` = 256 / chunks row slices (1 for the widest tile, 4 for the 256-column fp32 tile).
 __host__ __device__ inline int fused_slices(int tw, int elem_bytes) { return kFusedConsumers / (tw * elem_bytes / 16); }
+// Slab = [group][box][8 rows][256 columns]: box (g, b) holds rows 8g..8g+7, columns 256b..256b+255 of the tile.
 __host__ __device__ inline FusedSmem fused_layout(int rows, int tw, int elem_bytes) {
     FusedSmem L;
     const int ngroups = (rows + kGroup - 1) / kGroup;
     const int slices = fused_slices(tw, elem_bytes);
     L.slab = 0;
-    L.s_w = (size_t)rows * tw * elem_bytes;
+    L.s_w = (size_t)ngroups * kGroup * tw * elem_bytes;
     L.s_part = L.s_w + (size_t)tw * 4;                       // [slices][tw] partial updates (only when slices > 1)
     L.s_c = L.s_part + (slices > 1 ? (size_t)slices * tw * 4 : 0);
     L.s_acc = L.s_c + (size_t)ngroups * kGroup * 4;        // c and the accumulators are padded to whole groups
@@ -168,10 +135,12 @@ static int resident_ctas_fused(Kernel kernel, size_t smem) {
 
 template <typename BT, int CPT>
 __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm)
-cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const double* __restrict__ c_in,
+cgs_update_project_kernel(const __grid_constant__ CUtensorMap tmap, int rows, const double* __restrict__ c_in,
                           float* __restrict__ w, int64_t n, double* partials, unsigned* counter,
                           double* c_out, double* norm2_out) {
-    constexpr int TW = kFusedConsumers * CPT;
+    constexpr int TW = kFusedConsumers * CPT;               // tile width = CPT boxes
+    constexpr int kBoxElems = kGroup * kBoxCols;
+    constexpr uint32_t kBoxBytes = kBoxElems * sizeof(BT);
     extern __shared__ __align__(128) unsigned char smem[];
     const FusedSmem L = fused_layout(rows, TW, (int)sizeof(BT));
     BT* slab = reinterpret_cast<BT*>(smem + L.slab);
@@ -188,9 +157,7 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int g = 0; g < ngroups; ++g) {
-            const int rows_g = min(kGroup, rows - g * kGroup);
-            (void)rows_g;
-            mbar_init(&full[g], 1);                  // the producer's arrive.expect_tx (+ the bytes of the group's rows)
+            mbar_init(&full[g], CPT);                // one arrive.expect_tx per box of the group (+ the boxes' bytes)
             mbar_init(&empty[g], 1);                 // the owning consumer warp's release after pass B
         }
         mbar_fence_init();
@@ -201,27 +168,20 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
     }
     __syncthreads();
 
-    const int64_t ntiles_full = n / TW;
-    const int64_t ntiles = ntiles_full + ((n % TW) ? 1 : 0);
+    const int64_t ntiles = (n + TW - 1) / TW;
     float nrm = 0.0f;
 
     if (warp == kWarps) {
-        // ===== producer warp: every lane issues one row copy per step (4 row groups in flight per step) =====
-        // lane l serves row (l & 7) of group 4*q + (l >> 3).  The expect_tx may reach the barrier after some
-        // of the group's bytes have landed (the tx-count goes transiently negative, which PTX allows): the
-        // phase cannot complete before the single pending arrival -- the expect_tx itself -- has happened.
+        // ===== producer warp: one lane per (group, box); a lane waits for its group's slots, announces its
+        //       box's bytes on the group's barrier and issues the box =====
+        const int nitems = ngroups * CPT;
         uint32_t it = 0;
-        const int r = lane & 7;
-        for (int64_t tile = blockIdx.x; tile < ntiles_full; tile += gridDim.x, ++it) {
-            const BT* col0 = V + tile * TW;
-            for (int g = lane >> 3; g < ngroups; g += 4) {
-                const int rows_g = min(kGroup, rows - g * kGroup);
-                if (r < rows_g) {
-                    mbar_wait(&empty[g], (it & 1u) ^ 1u);          // slot group free (passes at once on the first tile)
-                    if (r == 0) mbar_arrive_expect_tx(&full[g], (uint32_t)(rows_g * TW * sizeof(BT)));
-                    const int i = g * kGroup + r;
-                    tma_bulk_g2s(slab + (size_t)i * TW, col0 + (int64_t)i * ldv, (uint32_t)(TW * sizeof(BT)), &full[g]);
-                }
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            for (int item = lane; item < nitems; item += 32) {
+                const int g = item / CPT, b = item - g * CPT;
+                mbar_wait(&empty[g], (it & 1u) ^ 1u);              // slot group free (passes at once on the first tile)
+                mbar_arrive_expect_tx(&full[g], kBoxBytes);
+                tma_box_g2s(slab + (size_t)item * kBoxElems, &tmap, (int)(tile * TW) + b * kBoxCols, g * kGroup, &full[g]);
             }
         }
     } else {
@@ -235,13 +195,15 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
         constexpr int S = kFusedConsumers / NQ;                 // row slices
         static_assert(NQ * S == kFusedConsumers && (S > 1 || E == CPT), "tile width / slice mapping");
         const int q = tid % NQ, slice = tid / NQ;
+        // element offset of this thread's chunk inside a group: box (q*E / 256), column (q*E % 256)
+        const int a_off = ((q * E) / kBoxCols) * kBoxElems + ((q * E) % kBoxCols);
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const bool manual = tile >= ntiles_full;               // ragged last tile: filled by hand, zero padded
             const int64_t x0 = tile * TW;
             const int valid = (int)((n - x0 < TW) ? (n - x0) : TW);
+            const bool whole = valid == TW;
             float acc[E];
-            if (slice == 0 && !manual) {
+            if (slice == 0 && whole) {
                 ld_f32<E>(w + x0 + q * E, acc);
             } else {
 #pragma unroll
@@ -250,45 +212,26 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
                     acc[e] = (slice == 0 && x < valid) ? w[x0 + x] : 0.0f;
                 }
             }
-            if (manual) {
-                consumer_bar();                                    // previous tile's pass B is over: slab is ours
-                for (int idx = tid; idx < rows * TW; idx += kFusedConsumers) {
-                    const int i = idx / TW, x = idx - i * TW;
-                    BT zero = BT(0);
-                    slab[idx] = x < valid ? V[(int64_t)i * ldv + x0 + x] : zero;
-                }
-                consumer_bar();
-            }
-            // ---- pass A: w' = w - sum_i c1[i] V[i, tile] ----
+            // ---- pass A: w' = w - sum_i c1[i] V[i, tile]  (rows >= `rows` are zeros with zero coefficients) ----
             for (int g = slice; g < ngroups; g += S) {
-                if (!manual) mbar_wait(&full[g], it & 1u);
+                mbar_wait(&full[g], it & 1u);
                 const int i0 = g * kGroup;
-                const int rows_g = min(kGroup, rows - i0);
                 const float4 ca = *reinterpret_cast<const float4*>(s_c + i0);       // 8 coefficients, 2 broadcasts
                 const float4 cb = *reinterpret_cast<const float4*>(s_c + i0 + 4);
                 const float cg[kGroup] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                const BT* col = slab + (size_t)i0 * TW + q * E;
-                if (rows_g == kGroup) {
-                    float v[kGroup][8];
+                const BT* col = slab + (size_t)g * (CPT * kBoxElems) + a_off;
+                float v[kGroup][8];
 #pragma unroll
-                    for (int r = 0; r < kGroup; ++r) Chunk16<BT>::load(col + r * TW, v[r]);   // all loads first ...
+                for (int r = 0; r < kGroup; ++r) Chunk16<BT>::load(col + r * kBoxCols, v[r]);   // all loads first ...
 #pragma unroll
-                    for (int r = 0; r < kGroup; ++r) {                                        // ... then the FMAs
+                for (int r = 0; r < kGroup; ++r) {                                              // ... then the FMAs
 #pragma unroll
-                        for (int e = 0; e < E; ++e) acc[e] = fmaf(cg[r], v[r][e], acc[e]);
-                    }
-                } else {
-                    for (int r = 0; r < rows_g; ++r) {
-                        float v[8];
-                        Chunk16<BT>::load(col + r * TW, v);
-#pragma unroll
-                        for (int e = 0; e < E; ++e) acc[e] = fmaf(s_c[i0 + r], v[e], acc[e]);
-                    }
+                    for (int e = 0; e < E; ++e) acc[e] = fmaf(cg[r], v[r][e], acc[e]);
                 }
             }
             if constexpr (S == 1) {
                 consumer_bar();                                    // nobody still reads s_w from the previous pass B
-                if (!manual) {
+                if (whole) {
                     st_f32<E>(w + x0 + q * E, acc);
                 } else {
 #pragma unroll
@@ -310,7 +253,7 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
 #pragma unroll
                     for (int c = 0; c < CPT; ++c) fin[c] += t[c];
                 }
-                if (!manual) {
+                if (whole) {
                     st_f32<CPT>(w + x0 + tid * CPT, fin);
                 } else {
 #pragma unroll
@@ -327,39 +270,32 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
             //      ONE 9-shuffle butterfly; then the group's slots go back to the producer. ----
             constexpr int NCH = TW / (32 * E);                      // chunks per lane per row
             float wr[NCH][E];
+            int b_off[NCH];
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
-                const float* src = s_w + (k * 32 + lane) * E;
-                const float4 a = *reinterpret_cast<const float4*>(src);
-                wr[k][0] = a.x; wr[k][1] = a.y; wr[k][2] = a.z; wr[k][3] = a.w;
-                if (E == 8) {
-                    const float4 b = *reinterpret_cast<const float4*>(src + 4);
-                    wr[k][4 % E] = b.x; wr[k][5 % E] = b.y; wr[k][6 % E] = b.z; wr[k][7 % E] = b.w;
-                }
+                const int x = (k * 32 + lane) * E;
+                ld_f32<E>(s_w + x, wr[k]);
+                b_off[k] = (x / kBoxCols) * kBoxElems + (x % kBoxCols);
             }
             const int my_row = warp_sum8_row(lane);
             for (int g = warp; g < ngroups; g += kWarps) {
-                const int i0 = g * kGroup;
-                const int rows_g = min(kGroup, rows - i0);
+                const BT* grp = slab + (size_t)g * (CPT * kBoxElems);
                 float p[kGroup];
 #pragma unroll
                 for (int r = 0; r < kGroup; ++r) {
                     p[r] = 0.0f;
-                    if (r < rows_g) {
-                        const BT* row = slab + (size_t)(i0 + r) * TW;
 #pragma unroll
-                        for (int k = 0; k < NCH; ++k) {
-                            float v[8];
-                            Chunk16<BT>::load(row + (k * 32 + lane) * E, v);
+                    for (int k = 0; k < NCH; ++k) {
+                        float v[8];
+                        Chunk16<BT>::load(grp + b_off[k] + r * kBoxCols, v);
 #pragma unroll
-                            for (int e = 0; e < E; ++e) p[r] = fmaf(v[e], wr[k][e], p[r]);
-                        }
+                        for (int e = 0; e < E; ++e) p[r] = fmaf(v[e], wr[k][e], p[r]);
                     }
                 }
                 const float tot = warp_sum8(p, lane);
-                if ((lane & 3) == 0 && my_row < rows_g) s_acc[i0 + my_row] += (double)tot;
+                if ((lane & 3) == 0) s_acc[g * kGroup + my_row] += (double)tot;
                 __syncwarp();                                       // every lane is done reading the group's rows
-                if (lane == 0 && !manual) mbar_arrive(&empty[g]);   // hand the group's slots back to the producer
+                if (lane == 0) mbar_arrive(&empty[g]);              // hand the group's slots back to the producer
             }
         }
     }
@@ -394,9 +330,44 @@ cgs_update_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn lookup_encode_tiled() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+}
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = lookup_encode_tiled();       // resolved once (thread-safe static)
+    return fn;
+}
+
+// The basis as the TMA unit sees it: [rows x n] elements, row pitch ldv, fetched in [8 x 256] boxes, zeros outside.
+template <typename BT>
+static int make_basis_map(CUtensorMap* map, const BT* V, int64_t ldv, int rows, int64_t n, const char* name) {
+    EncodeTiledFn enc = encode_tiled();
+    HLV_REQUIRE(enc != nullptr, HLV_ERR_NO_DEVICE, "%s: cuTensorMapEncodeTiled is not available from this driver", name);
+    const cuuint64_t gdim[2] = {(cuuint64_t)(n > 0 ? n : 1), (cuuint64_t)rows};   // n == 0: no tile is ever requested
+    const cuuint64_t gstride[1] = {(cuuint64_t)ldv * sizeof(BT)};
+    const cuuint32_t box[2] = {(cuuint32_t)kBoxCols, (cuuint32_t)kGroup};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = enc(map, sizeof(BT) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                           const_cast<BT*>(V), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HLV_REQUIRE(r == CUDA_SUCCESS, HLV_ERR_ARG, "%s: cuTensorMapEncodeTiled failed (CUresult %d) for rows=%d n=%lld ldv=%lld",
+                name, (int)r, rows, (long long)n, (long long)ldv);
+    return HLV_OK;
+}
+
 // Widest tile (columns) whose slab fits; 0 if even the narrowest does not.
-// Slab budget per CTA.  Default 100 KB = two CTAs per SM; HLV_FUSED_SLAB_KB (tuning knob, read once) can raise
-// it to ~200 KB = one CTA per SM with a tile twice as wide.
+// Slab budget per CTA.  Default 104 KB = two CTAs per SM; HLV_FUSED_SLAB_KB (tuning knob, read once) can raise
+// it to ~208 KB = one CTA per SM with a tile twice as wide.
 static size_t slab_budget() {
     static size_t budget = 0;
     if (budget == 0) {
@@ -409,9 +380,10 @@ static size_t slab_budget() {
 
 template <typename BT>
 static int pick_cpt(int rows) {
-    const int max_cpt = sizeof(BT) == 4 ? 4 : 8;          // keeps pass-A shared-memory reads conflict-free
+    const int max_cpt = sizeof(BT) == 4 ? 4 : 8;          // one 16-byte chunk per thread per row at the widest
+    const int rows_pad = (rows + kGroup - 1) / kGroup * kGroup;          // the slab holds whole 8-row boxes
     for (int cpt = max_cpt; cpt >= 1; cpt >>= 1)
-        if ((size_t)rows * kFusedConsumers * cpt * sizeof(BT) <= slab_budget()) return cpt;
+        if ((size_t)rows_pad * kFusedConsumers * cpt * sizeof(BT) <= slab_budget()) return cpt;
     return 0;
 }
 
@@ -423,7 +395,10 @@ static int launch_fused(const BT* V, int64_t ldv, int rows, const double* c_in, 
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(update_project)");
     const int64_t tw = kFusedConsumers * CPT;
     const int grid = persistent_grid((n + tw - 1) / tw, resident_ctas_fused(cgs_update_project_kernel<BT, CPT>, smem));
-    cgs_update_project_kernel<BT, CPT><<<grid, kFusedThreads, smem, stream>>>(V, ldv, rows, c_in, w, n, ws.partials, ws.counters,
+    CUtensorMap map;
+    const int rc = make_basis_map<BT>(&map, V, ldv, rows, n, name);
+    if (rc != HLV_OK) return rc;
+    cgs_update_project_kernel<BT, CPT><<<grid, kFusedThreads, smem, stream>>>(map, rows, c_in, w, n, ws.partials, ws.counters,
                                                                               c_out, norm2_out);
     HLV_LAUNCH_CHECK(name);
     return HLV_OK;
@@ -460,7 +435,7 @@ extern "C" {
 
 int hlv_cgs_fused_max_rows(int elem_bytes) {
     if (elem_bytes != 2 && elem_bytes != 4) return 0;
-    return (int)(slab_budget() / (size_t)(kFusedConsumers * elem_bytes));
+    return (int)(slab_budget() / (size_t)(kFusedConsumers * elem_bytes)) / kGroup * kGroup;
 }
 
 int hlv_cgs_update_project_f32(const float* V, int64_t ldv, int rows, const double* c_in, float* w, int64_t n,

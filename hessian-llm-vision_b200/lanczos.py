@@ -235,12 +235,12 @@ class LanczosEngine:
         self.breakdown_iter = torch.full((1,), -1, dtype=torch.int32, device=self.device)
         self.ws = ops.Workspace(self.device, max_rows=max(m, 1) + 1)
         # fused middle pass of CGS2 (TMA-staged slab, basis read 3x instead of 4x per iteration)
-        # Measured policy (profiles/r01_cgs_kernels.json): a win for fp32 rows from ~8 rows up; bf16 rows carry
-        # twice the FMAs per byte and the unfused pair is faster there.  fused_cgs="force" overrides.
-        want = fused_cgs == "force" or (bool(fused_cgs) and basis_dtype == torch.float32)
+        # Measured policy (profiles/r01_cgs_kernels.json): 1.5-1.9x over the update+project pair for fp32 rows
+        # and 1.2-1.5x for bf16 rows; break-even near 4 rows.  fused_cgs="force" uses it from 1 row.
+        want = fused_cgs == "force" or bool(fused_cgs)
         self.fused = want and self.keep_basis and hasattr(ops, "cgs_update_project")
         self.fused_max_rows = ops.fused_max_rows(basis_dtype) if self.fused else 0
-        self.fused_min_rows = 1 if fused_cgs == "force" else 8
+        self.fused_min_rows = 1 if fused_cgs == "force" else 4
         self.j = 0
         self.launches = 0
 
