@@ -31,8 +31,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+# Rank 0 prints ONE JSON line on stdout and nothing else: keep a private handle to the real stdout and point
+# fd 1 at stderr, so whatever a library writes to stdout (NCCL's version banner, warnings) lands in stderr.
+_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
 
 import torch  # noqa: E402
 
@@ -59,6 +67,10 @@ def parse_args():
     ap.add_argument("--no-fused", action="store_true", help="CGS2 as 4 separate passes (project, update, project, update)")
     ap.add_argument("--extras", action="store_true", help="also time the cached / CUDA-graph HVP modes (reported under 'extras')")
     ap.add_argument("--cache-graph", action="store_true", help="keep the first-backward graph across iterations (extra, not the headline)")
+    ap.add_argument("--hvp-mode", default="graph", choices=["graph", "eager"],
+                    help="graph: the whole double-backward (forward, both backward passes, gather) is captured once into a CUDA "
+                         "graph and replayed every iteration -- all of the work, none of the ~4,000 Python-issued launches; "
+                         "eager: issue it from Python every iteration like the reference")
     ap.add_argument("--small", action="store_true", help="tiny model for a functional check of this script (NOT a benchmark)")
     return ap.parse_args()
 
@@ -224,7 +236,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "clocks": clocks.stop(), "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bench_config(args, seq, n):
@@ -257,6 +269,21 @@ def run_ours(args, rank, world, local_rank):
     mine_dev = [b.to(dev) for b in mine_host]
     op_dev = hlv.HessianVectorProduct(model, mine_dev, total_sequences=args.global_batch, cache_graph=args.cache_graph)
     op_host = hlv.HessianVectorProduct(model, mine_host, total_sequences=args.global_batch, device=dev)
+    hvp_modes = {}
+
+    def graphed(op, tag):
+        """The operator the timed loop uses: the same double-backward, replayed from a CUDA graph (or eager)."""
+        if args.hvp_mode != "graph":
+            hvp_modes[tag] = "eager"
+            return op
+        try:
+            g = op.capture(out=eng.w if world == 1 else eng.hv_full)
+            hvp_modes[tag] = "cuda_graph (forward + both backward passes + gather replayed every iteration)"
+            return g
+        except Exception as e:  # noqa: BLE001  -- a model that cannot be captured still benches, eagerly
+            hvp_modes[tag] = f"eager (capture failed: {repr(e)[:200]})"
+            torch.cuda.synchronize()
+            return op
     basis_dtype = torch.float32 if args.basis_dtype == "f32" else torch.bfloat16
     eng = hlv.LanczosEngine(op_dev, n, M_DEPTH, dev, reorth="full", basis_dtype=basis_dtype, comm=comm, profile=True,
                             fused_cgs=not args.no_fused)
@@ -309,12 +336,13 @@ def run_ours(args, rank, world, local_rank):
             eng.v_full.normal_(generator=g).mul_(1.0 / n ** 0.5)
     else:
         prefill()
-    eng.hvp = op_dev
+    run_dev = graphed(op_dev, "value")
+    eng.hvp = run_dev
     for i in range(max(args.warmup, 0)):
         eng.step(sched[i % len(sched)])
     torch.cuda.synchronize()
 
-    ms, launches, clocks, phases = timed(op_dev, e2e=False)
+    ms, launches, clocks, phases = timed(run_dev, e2e=False)
     value = args.steps / (ms / 1e3)
     ritz_top = None
     if real_run:
@@ -322,13 +350,24 @@ def run_ours(args, rank, world, local_rank):
         ritz_top = [float(x) for x in res.eigvals[-3:]]
 
     e2e = None
+    del run_dev
+    eng.hvp = op_dev
+    torch.cuda.empty_cache()
     if not args.no_e2e:
+        run_host = graphed(op_host, "e2e")
+        eng.hvp = run_host
+        for i in range(min(max(args.warmup, 0), 1)):
+            eng.step(sched[i % len(sched)])
         h2d0 = op_host.h2d_bytes
-        ms_e, _, _, _ = timed(op_host, e2e=True)
+        ms_e, _, _, _ = timed(run_host, e2e=True)
+        del run_host
+        eng.hvp = op_dev
+        torch.cuda.empty_cache()
         e2e = {"value": args.steps / (ms_e / 1e3), "unit": "iterations/s",
                "h2d_bytes_per_step": (op_host.h2d_bytes - h2d0) // args.steps, "d2h_bytes_per_step": 16,
                "ms_per_step": ms_e / args.steps,
-               "api": "LanczosEngine.step over HessianVectorProduct with pinned-host token batches; alpha/beta read back every step"}
+               "api": "LanczosEngine.step over HessianVectorProduct with pinned-host token batches (copied H2D inside every "
+                      "application); alpha/beta read back every step", "hvp_mode": hvp_modes.get("e2e")}
 
     # ---- extras (NOT the headline): the product's faster HVP modes, same metric, same steps --------------
     # The headline arms above rebuild the whole double-backward every iteration, exactly like the reference.
@@ -391,7 +430,7 @@ def run_ours(args, rank, world, local_rank):
                                 "note": "sum of libhlv kernel time (CUDA events) in the timed region; HVP (torch) excluded"},
             "hvp_ms_per_step": phases.get("hvp", {}).get("ms", 0.0) / args.steps,
             "phases_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in phases.items()},
-            "ritz_top3": ritz_top, "extras": extras}
+            "hvp_mode": hvp_modes.get("value"), "ritz_top3": ritz_top, "extras": extras}
     # ---- CPU baseline: the reference's CPU path on this box's host cores (rank 0, N=1 only) ----
     if world == 1 and not args.no_cpu_baseline:
         del eng
@@ -409,7 +448,7 @@ def run_ours(args, rank, world, local_rank):
                                 "sample": f"{reps} iterations of the gpt2_hessian_cpu.py shape (GPU HVP + .cpu() + host recurrence {t_fix:.2f}s; "
                                           f"host CGS2 on {host_rows} rows {t_cgs:.2f}s scaled linearly to the m=100 mean depth {mean_rows:.1f} rows)",
                                 "os_cpu_count": os.cpu_count()}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():

@@ -32,7 +32,7 @@ def lm_loss(model, batch):
     """``model(input_ids=ids, labels=ids).loss`` -- labels are the inputs, no padding mask
     (gpt2_hessian_cpu.py:94-97; quirk Q9)."""
     ids = batch["input_ids"] if isinstance(batch, dict) else batch
-    loss = model(input_ids=ids, labels=ids).loss
+    loss = model(input_ids=ids, labels=ids, use_cache=False).loss      # no KV cache: same loss, nothing to allocate
     return loss.mean() if loss.dim() > 0 else loss
 
 
@@ -68,6 +68,31 @@ def _math_sdpa():
         return sdpa_kernel(SDPBackend.MATH)
     except Exception:  # pragma: no cover
         return contextlib.nullcontext()
+
+
+@contextlib.contextmanager
+def _capturable_scalar_tensors():
+    """``torch.tensor(<python scalar>, device=cuda)`` is a pageable host-to-device copy, which is illegal while
+    a CUDA graph is being captured -- and transformers' eager-attention mask builder does exactly that
+    (masking_utils.eager_mask: ``torch.tensor(0.0, device=mask.device, dtype=dtype)``).  While capturing, such
+    0-dim constants are produced by a fill kernel instead (same value, same dtype rules)."""
+    orig = torch.tensor
+
+    def tensor(data, *args, **kwargs):
+        dev = kwargs.get("device")
+        if isinstance(data, (bool, int, float)) and not args and dev is not None and torch.device(dev).type == "cuda":
+            dtype = kwargs.get("dtype")
+            if dtype is None:
+                dtype = torch.bool if isinstance(data, bool) else (torch.int64 if isinstance(data, int) else torch.get_default_dtype())
+            out = torch.full((), data, dtype=dtype, device=dev)
+            return out.requires_grad_(True) if kwargs.get("requires_grad") else out
+        return orig(data, *args, **kwargs)
+
+    torch.tensor = tensor
+    try:
+        yield
+    finally:
+        torch.tensor = orig
 
 
 def shard_batches(batches: Sequence, rank: int, world: int) -> List:
@@ -201,11 +226,14 @@ class HessianVectorProduct:
     def clear_cache(self) -> None:
         self._graphs.clear()
 
-    def capture(self, ws=None, warmup: int = 3) -> "GraphedHVP":
+    def capture(self, ws=None, warmup: int = 3, out: Optional[torch.Tensor] = None) -> "GraphedHVP":
         """Capture one full application (every micro-batch's forward, both backward passes and the
-        libhlv gather + fused <Hv, v>) into a CUDA graph.  Worth it when the per-rank batch is small
-        and the ~3,000 launches of a double-backward are host-bound (strong scaling at 4-8 GPUs)."""
-        return GraphedHVP(self, ws=ws, warmup=warmup)
+        libhlv gather + fused <Hv, v>) into a CUDA graph; a replay redoes ALL of that work, only the
+        ~4,000 kernel launches per double-backward are no longer issued from Python.  Worth most when
+        the per-rank batch is small and the launches are host-bound (strong scaling at 4-8 GPUs).
+        Batches may live in pinned host memory: their H2D copies become nodes of the graph.
+        ``out``: write H v straight into this buffer (e.g. the engine's w) instead of a private one."""
+        return GraphedHVP(self, ws=ws, warmup=warmup, out=out)
 
 
 class GraphedHVP:
@@ -216,16 +244,23 @@ class GraphedHVP:
     graph is replayed, and the result is copied out (or the graph's output buffer is handed to the
     engine directly when it asks for it via ``out_buffer``)."""
 
-    def __init__(self, op: "HessianVectorProduct", ws=None, warmup: int = 3):
+    def __init__(self, op: "HessianVectorProduct", ws=None, warmup: int = 3, out: Optional[torch.Tensor] = None):
         from . import kernels
-        if any(_first(b).device != op.device for b in op.batches):
-            raise ValueError("capture() needs device-resident batches")
+        for b in op.batches:
+            t = _first(b)
+            if t.device != op.device and not (t.device.type == "cpu" and t.is_pinned()):
+                raise ValueError("capture() needs device-resident or pinned-host batches")
         self.op = op
         self.n = op.n
         dev = op.device
         self.ws = ws if ws is not None else kernels.Workspace(dev, max_rows=1)
         self.v = torch.zeros(op.n, dtype=torch.float32, device=dev)
-        self.out = torch.zeros(op.n, dtype=torch.float32, device=dev)
+        if out is not None:
+            if out.device != dev or out.dtype != torch.float32 or out.numel() < op.n or not out.is_contiguous():
+                raise ValueError("capture(out=...): need a contiguous float32 device buffer of at least n elements")
+            self.out = out.reshape(-1)[: op.n]
+        else:
+            self.out = torch.zeros(op.n, dtype=torch.float32, device=dev)
         self.dot = torch.zeros(1, dtype=torch.float64, device=dev)
         self.v.normal_()
         self.v /= torch.linalg.vector_norm(self.v)
@@ -238,21 +273,26 @@ class GraphedHVP:
         op.clear_cache()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), _capturable_scalar_tensors():
             for _ in range(max(1, warmup)):
                 run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        before = kernels.launch_count
-        with torch.cuda.graph(self.graph):
+        before, h2d0 = kernels.launch_count, op.h2d_bytes
+        with torch.cuda.graph(self.graph), _capturable_scalar_tensors():
             run()
         self.launches_per_replay = kernels.launch_count - before
+        self.h2d_bytes_per_replay = op.h2d_bytes - h2d0     # pinned-host batches: copied by the graph on every replay
         self.applications = 0
 
     @property
     def weights(self):
         return self.op.weights
+
+    @property
+    def h2d_bytes(self):
+        return self.op.h2d_bytes
 
     def accumulate_into(self, v: torch.Tensor, out: torch.Tensor, dot_with=None, dot_out=None,
                         ws=None, ops=None, phases=None) -> None:
@@ -260,6 +300,7 @@ class GraphedHVP:
         self.v.copy_(v.reshape(-1))
         self.graph.replay()
         kernels.launch_count += self.launches_per_replay
+        self.op.h2d_bytes += self.h2d_bytes_per_replay
         if out.data_ptr() != self.out.data_ptr():
             out.copy_(self.out)
         if dot_out is not None:

@@ -304,3 +304,29 @@ def test_ritz_vectors(K, cuda_dev, dtype, m, nvec, n):
     K.ritz_vectors(Q, m, Y, out, n)
     ref = Y.double().t() @ Q[:, :n].double()                     # eigvects.t() @ Q
     assert float((out[:, :n].double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("m,k,n", [(6, 6, 1000), (24, 5, 70_003)])
+def test_adjust_implicit_equals_explicit_ritz_vectors(K, cuda_dev, dtype, m, k, n):
+    """g += Q^T (Y diag(s) Y^T) (Q g) (two passes over the Lanczos basis) equals forming the k Ritz vectors
+    V = Y^T Q (gpt2_hessian_cpu.py:217) and applying the reference's adjustment (:224-229) to them."""
+    from hessian_llm_vision_b200 import adjust
+    Q, _ = _basis(m, n, cuda_dev, dtype, 3 * m + n)
+    g = torch.Generator(device=cuda_dev).manual_seed(m + n)
+    A = torch.randn(m, m, device=cuda_dev, generator=g, dtype=torch.float64)
+    lam, Y = torch.linalg.eigh(A + A.t())
+    lam = lam.abs() + 0.5
+    grad = torch.randn(n, device=cuda_dev, generator=g)
+    delta = 0.05
+    sel = list(range(m - k, m))                                   # the k largest, as the reference keeps them
+    got = adjust.adjust_gradient_implicit(grad, Q, m, Y, lam, delta, select=sel)
+    Vr = (Y[:, sel].t() @ Q[:, :n].double()).float()             # explicit Ritz vectors (fp64 product of the stored rows)
+    ref = oracle.lowrank_adjust(grad.cpu(), Vr.cpu(), lam[sel].float().cpu(), delta)
+    assert float((got.cpu() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    # in place, all pairs
+    out = grad.clone()
+    adjust.adjust_gradient_implicit(out, Q, m, Y, lam, delta, out=out)
+    Va = (Y.t() @ Q[:, :n].double()).float()
+    ref_all = oracle.lowrank_adjust(grad.cpu(), Va.cpu(), lam.float().cpu(), delta)
+    assert float((out.cpu() - ref_all).abs().max()) <= 2e-5 * float(ref_all.abs().max())

@@ -258,6 +258,37 @@ def test_cuda_graph_replayed_operator(hlv, cuda_dev, golden_dir):
     assert _rel(graphed.T, eager.T, float(eager.T.abs().max())) < 1e-5
 
 
+def test_cuda_graph_full_double_backward(hlv, cuda_dev, golden_dir):
+    """capture() of the plain operator: forward + first backward + second backward + gather are ALL inside the
+    graph (nothing is cached between applications); pinned-host batches are copied by the graph on every replay;
+    ``out=`` writes Hv into a caller's buffer."""
+    g = np.load(os.path.join(golden_dir, "tiny_gpt2_hvp.npz"))
+    model = _tiny_model(g).to(cuda_dev)
+    vec = torch.from_numpy(g["vec"]).to(cuda_dev)
+    hv_ref = torch.from_numpy(g["hv"])
+    scale = float(hv_ref.abs().max())
+    ids_host = torch.from_numpy(g["ids"]).pin_memory()
+    for batches in ([ids_host.to(cuda_dev)], [ids_host]):
+        op = hlv.HessianVectorProduct(model, batches, device=cuda_dev)
+        buf = torch.full((vec.numel() + 8,), float("nan"), device=cuda_dev)
+        gop = op.capture(out=buf)
+        assert not op._graphs                                  # nothing kept from the first backward
+        for _ in range(2):
+            assert _rel(gop(vec), hv_ref, scale) < 2e-5
+        assert _rel(buf[: vec.numel()], hv_ref, scale) < 2e-5
+        hv2 = gop(2 * vec)                                       # a different input really is recomputed
+        assert _rel(hv2, 2 * hv_ref, 2 * scale) < 2e-5
+    assert gop.h2d_bytes_per_replay == ids_host.numel() * ids_host.element_size()
+    h0 = gop.h2d_bytes
+    gop(vec)
+    assert gop.h2d_bytes - h0 == gop.h2d_bytes_per_replay
+    eager = hlv.lanczos(hlv.HessianVectorProduct(model, [ids_host.to(cuda_dev)]), 10, vec, reorth="full")
+    graphed = hlv.lanczos(gop, 10, vec, reorth="full")
+    assert _rel(graphed.T, eager.T, float(eager.T.abs().max())) < 1e-5
+    with pytest.raises(ValueError, match="pinned"):
+        hlv.HessianVectorProduct(model, [torch.from_numpy(g["ids"])], device=cuda_dev).capture()
+
+
 def test_block_and_per_tensor_operators(hlv, cuda_dev, golden_dir):
     g = np.load(os.path.join(golden_dir, "tiny_gpt2_hvp.npz"))
     model_cpu = _tiny_model(g)
