@@ -119,10 +119,15 @@ int hlv_cgs_update_bf16(const uint16_t* V, int64_t ldv, int rows, const double* 
                         void* ws, size_t ws_bytes, hlv_stream_t stream);
 
 /* Fused middle pass of two-pass Gram-Schmidt: w -= V^T c_in ; c_out = V w_new ; norm2_out = |w_new|^2,
- * reading V from HBM once (a [rows x tile] slab is staged in shared memory by TMA bulk copies and used
- * for both the update and the projection).  CGS2 = project, update_project, update: 3 passes over V
- * instead of 4.  rows <= hlv_cgs_fused_max_rows(sizeof(elem)) (100 fp32 / 200 bf16: two 100 KB slabs
- * per SM); ws must hold rows+1 partial rows: hlv_workspace_bytes(rows + 1). */
+ * reading V from HBM once (a [rows x tile] slab is staged in shared memory by 2-D tiled TMA boxes of
+ * [8 rows x 256 columns] and used for both the update and the projection).  CGS2 = project,
+ * update_project, update: 3 passes over V instead of 4.  rows <= hlv_cgs_fused_max_rows(sizeof(elem))
+ * (104 fp32 / 208 bf16: two 104 KB slabs per SM); ws must hold rows+1 partial rows:
+ * hlv_workspace_bytes(rows + 1).  The launch encodes a CUtensorMap for V on the host
+ * (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint: no allocation, no synchronisation), so V must
+ * stay 16-byte aligned with ldv*sizeof(elem) a multiple of 16.
+ * Replaces: the second/third sweep of the reference's reorthogonalisation loop
+ * (Lanczos_Scratch/Discrepancy.ipynb cell 1:44-45 applied twice). */
 int hlv_cgs_fused_max_rows(int elem_bytes);
 int hlv_cgs_update_project_f32 (const float*    V, int64_t ldv, int rows, const double* c_in,
                                 float* w, int64_t n, double* c_out, double* norm2_out,
