@@ -20,6 +20,7 @@
 // being projected.  8 consumer warps: pass A "thread owns a 16-byte chunk of a row slice", pass B "warp
 // owns row groups" (fixed-order reductions).
 #include <cuda.h>        // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through the runtime
+#include <limits.h>
 #include <stdlib.h>
 
 #include "hlv_common.cuh"
@@ -411,6 +412,8 @@ static int update_project(const char* name, const BT* V, int64_t ldv, int rows, 
     HLV_REQUIRE(ldv >= n, HLV_ERR_ARG, "%s: ldv=%lld < n=%lld", name, (long long)ldv, (long long)n);
     HLV_REQUIRE(aligned16(V) && aligned16(w) && ((ldv * (int64_t)sizeof(BT)) & 15) == 0, HLV_ERR_ALIGN,
                 "%s: V, w must be 16-byte aligned and ldv*sizeof(elem) a multiple of 16", name);
+    HLV_REQUIRE(n <= (int64_t)INT32_MAX - 4096, HLV_ERR_ARG,
+                "%s: n=%lld exceeds the 32-bit TMA tile coordinates; shard the vector or use project+update", name, (long long)n);
     const int cpt = pick_cpt<BT>(rows);
     HLV_REQUIRE(cpt > 0, HLV_ERR_ARG, "%s: rows=%d exceeds the fused kernel's shared-memory slab (max %d); use project+update",
                 name, rows, hlv_cgs_fused_max_rows((int)sizeof(BT)));

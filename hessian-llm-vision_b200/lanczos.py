@@ -238,7 +238,8 @@ class LanczosEngine:
         # Measured policy (profiles/r01_cgs_kernels.json): 1.5-1.9x over the update+project pair for fp32 rows
         # and 1.2-1.5x for bf16 rows; break-even near 4 rows.  fused_cgs="force" uses it from 1 row.
         want = fused_cgs == "force" or bool(fused_cgs)
-        self.fused = want and self.keep_basis and hasattr(ops, "cgs_update_project")
+        self.fused = (want and self.keep_basis and hasattr(ops, "cgs_update_project")
+                      and sn < 2 ** 31 - 4096)            # the fused pass addresses tiles with 32-bit TMA coordinates
         self.fused_max_rows = ops.fused_max_rows(basis_dtype) if self.fused else 0
         self.fused_min_rows = 1 if fused_cgs == "force" else 4
         self.j = 0

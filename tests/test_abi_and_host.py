@@ -282,3 +282,31 @@ def test_slq_multi_probe_and_block_drivers(golden_dir):
     ref = oracle.lanczos_cgs2(lambda v: oracle.hess_vec_subset(v, [ids], model, blk), hlv.probe_vector(nb, 6, "cpu"), 4, reorth="full")
     ev_ref = torch.linalg.eigvalsh(ref["T"].double())
     assert float((ev[1].double() - ev_ref).abs().max()) < 1e-4 * float(ev_ref.abs().max())
+
+
+def test_capturable_scalar_tensors_patch_is_scoped():
+    """hvp._capturable_scalar_tensors only touches python-scalar constants aimed at a CUDA device (what
+    transformers' eager mask builder creates inside a CUDA-graph capture) and restores torch.tensor on exit."""
+    from hessian_llm_vision_b200 import hvp
+    orig = torch.tensor
+    with hvp._capturable_scalar_tensors():
+        assert torch.tensor is not orig
+        a = torch.tensor(0.0, device="cpu", dtype=torch.float64)           # CPU: untouched path
+        b = torch.tensor([1, 2, 3])                                        # sequences: untouched path
+        c = torch.tensor(3)
+        assert a.dtype == torch.float64 and a.item() == 0.0 and b.tolist() == [1, 2, 3] and c.dtype == torch.int64
+    assert torch.tensor is orig
+    with pytest.raises(RuntimeError):
+        with hvp._capturable_scalar_tensors():
+            raise RuntimeError("x")
+    assert torch.tensor is orig
+
+
+def test_lm_loss_disables_kv_cache_without_changing_the_loss():
+    from transformers import GPT2Config, GPT2LMHeadModel
+    from hessian_llm_vision_b200 import hvp
+    torch.manual_seed(0)
+    model = GPT2LMHeadModel(GPT2Config(vocab_size=61, n_positions=16, n_embd=16, n_layer=1, n_head=2,
+                                       attn_implementation="eager")).eval()
+    ids = torch.randint(0, 61, (2, 16))
+    assert torch.equal(hvp.lm_loss(model, ids), model(input_ids=ids, labels=ids).loss)
