@@ -65,7 +65,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="CGS2 as 4 separate passes (project, update, project, update)")
-    ap.add_argument("--extras", action="store_true", help="also time the cached / CUDA-graph HVP modes (reported under 'extras')")
+    ap.add_argument("--extras", action="store_true", help="also time the cached-first-backward HVP modes (reported under 'extras'); default at N=1")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--blas", default="default", choices=["default", "cublas", "cublaslt"],
+                    help="torch.backends.cuda.preferred_blas_library for the HVP's fp32 GEMMs (probe; fp32 either way)")
     ap.add_argument("--cache-graph", action="store_true", help="keep the first-backward graph across iterations (extra, not the headline)")
     ap.add_argument("--hvp-mode", default="graph", choices=["graph", "eager"],
                     help="graph: the whole double-backward (forward, both backward passes, gather) is captured once into a CUDA "
@@ -257,6 +260,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
+    if args.blas != "default":
+        torch.backends.cuda.preferred_blas_library(args.blas)
     comm = hlv.Comm()
     model, cfg = build_model(args.small)
     model.to(dev)
@@ -374,7 +379,7 @@ def run_ours(args, rank, world, local_rank):
     # The first-backward graph does not depend on v, so the operator can keep it (cache_graph=True) and an
     # iteration then costs one second-backward pass; that pass can additionally be replayed from a CUDA graph.
     extras = {}
-    if args.extras:
+    if (args.extras or world == 1) and not args.no_extras:
         try:
             op_c = hlv.HessianVectorProduct(model, mine_dev, total_sequences=args.global_batch, cache_graph=True)
             op_c.clear_cache()
