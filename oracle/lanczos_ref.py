@@ -118,14 +118,15 @@ def lanczos_cgs2(matvec: Matvec, v0: torch.Tensor, m: int,
     m=k+1 the T/Q equal ``hand_lanczos(…, k)`` bit for bit.
     """
     n = v0.numel()
-    alphas = torch.zeros(m, dtype=dtype)
-    betas = torch.zeros(m, dtype=dtype)
-    Q = torch.zeros(m, n, dtype=dtype)
+    where = v0.device                       # CPU in the tests; a CUDA device only for the full-size evidence runs
+    alphas = torch.zeros(m, dtype=dtype, device=where)
+    betas = torch.zeros(m, dtype=dtype, device=where)
+    Q = torch.zeros(m, n, dtype=dtype, device=where)
     store = (lambda x: bf16_round(x)) if basis_dtype == torch.bfloat16 else (lambda x: x)
     v = v0.to(dtype).clone()
     Q[0] = store(v)
     v_old = torch.zeros_like(v)
-    beta = torch.zeros((), dtype=dtype)
+    beta = torch.zeros((), dtype=dtype, device=where)
     m_eff = m
     for j in range(m):
         w = matvec(v).to(dtype).clone()
@@ -148,7 +149,7 @@ def lanczos_cgs2(matvec: Matvec, v0: torch.Tensor, m: int,
             v_old = v
             v = w / beta
             Q[j + 1] = store(v)
-    T = torch.zeros(m_eff, m_eff, dtype=dtype)
+    T = torch.zeros(m_eff, m_eff, dtype=dtype, device=where)
     for j in range(m_eff):
         T[j, j] = alphas[j]
         if j + 1 < m_eff:
