@@ -181,7 +181,8 @@ def test_cgs_project_update(K, cuda_dev, dtype, rows, n):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("rows,n", [(1, 1), (1, 300), (3, 2048), (8, 4096), (9, 2048 * 3 + 5), (26, 1_000_003), (50, 300_000),
-                                    (51, 300_000), (100, 65536 + 17), (100, 2_000_000), (101, 70_000), (200, 40_000)])
+                                    (51, 300_000), (100, 65536 + 17), (100, 2_000_000), (101, 70_000), (104, 70_001), (200, 40_000), (208, 3_001),
+                                    (57, 255), (12, 257)])
 def test_cgs_update_project_fused(K, cuda_dev, dtype, rows, n):
     """Fused middle pass of CGS2 (TMA-staged slab): w' = w - V^T c ; c2 = V w' ; |w'|^2 in one read of V,
     vs fp64 and vs the unfused update + project pair (same inputs)."""
