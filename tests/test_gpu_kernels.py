@@ -264,6 +264,21 @@ def test_cgs2_orthogonalises_full_size(K, cuda_dev):
     w2 = w.clone()
     K.cgs_update(V, rows, c, w2, nrm, ws)
     assert float((w2 - w).abs().max()) <= 1e-6 * float(w.abs().max())   # idempotent
+    # the same CGS2 as 3 passes (fused middle pass, 2-D TMA slab) at full size: same properties, same result
+    w3 = torch.randn(n, device=cuda_dev, generator=torch.Generator(device=cuda_dev).manual_seed(99))
+    w4 = w3.clone()
+    c2 = torch.zeros_like(c)
+    ws1 = _ws(K, cuda_dev, rows + 1)
+    K.cgs_project(V, rows, w3, c, ws1)
+    K.cgs_update_project(V, rows, c, w3, c2, nrm, ws1)
+    K.cgs_update(V, rows, c2, w3, nrm, ws1)
+    for _ in range(2):
+        K.cgs_project(V, rows, w4, c, ws)
+        K.cgs_update(V, rows, c, w4, nrm, ws)
+    assert float((w3 - w4).abs().max()) <= 2e-6 * float(w4.abs().max())
+    K.cgs_project(V, rows, w3, c, ws)
+    assert float(c.abs().max()) < 1e-5 * float(torch.linalg.vector_norm(w3.double()))
+    assert abs(nrm.item() - float(w4.double() @ w4.double())) <= 1e-6 * nrm.item()
 
 
 # ------------------------------------------------------------------ vector_adjust / Ritz vectors
