@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--blas", default="default", choices=["default", "cublas", "cublaslt"],
                     help="torch.backends.cuda.preferred_blas_library for the HVP's fp32 GEMMs (probe; fp32 either way)")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="graph mode: one graph per application instead of two (v-independent half prefetched on a side stream "
+                         "while the recurrence of the previous iteration runs)")
     ap.add_argument("--cache-graph", action="store_true", help="keep the first-backward graph across iterations (extra, not the headline)")
     ap.add_argument("--hvp-mode", default="graph", choices=["graph", "eager"],
                     help="graph: the whole double-backward (forward, both backward passes, gather) is captured once into a CUDA "
@@ -282,8 +285,10 @@ def run_ours(args, rank, world, local_rank):
             hvp_modes[tag] = "eager"
             return op
         try:
-            g = op.capture(out=eng.w if world == 1 else eng.hv_full)
-            hvp_modes[tag] = "cuda_graph (forward + both backward passes + gather replayed every iteration)"
+            pipe = not args.no_pipeline
+            g = op.capture(out=eng.w if world == 1 else eng.hv_full, pipeline=pipe)
+            hvp_modes[tag] = ("cuda_graph (forward + both backward passes + gather replayed every iteration"
+                              + ("; the v-independent half of iteration j+1 overlaps the recurrence of iteration j on a side stream)" if pipe else ")"))
             return g
         except Exception as e:  # noqa: BLE001  -- a model that cannot be captured still benches, eagerly
             hvp_modes[tag] = f"eager (capture failed: {repr(e)[:200]})"
@@ -326,6 +331,8 @@ def run_ours(args, rank, world, local_rank):
             eng.step(j)
             if e2e:                                       # device -> host read of the step's result (alpha_j, beta_{j+1})
                 sink += float(eng.alphas[j].item()) + float(eng.betas[j + 1].item())
+        if hasattr(op, "drain"):
+            op.drain()                                    # a prefetched half-application is work of this region: wait for it
         ev1.record()
         torch.cuda.synchronize(); comm.barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)

@@ -226,14 +226,19 @@ class HessianVectorProduct:
     def clear_cache(self) -> None:
         self._graphs.clear()
 
-    def capture(self, ws=None, warmup: int = 3, out: Optional[torch.Tensor] = None) -> "GraphedHVP":
+    def capture(self, ws=None, warmup: int = 3, out: Optional[torch.Tensor] = None, pipeline: bool = False) -> "GraphedHVP":
         """Capture one full application (every micro-batch's forward, both backward passes and the
         libhlv gather + fused <Hv, v>) into a CUDA graph; a replay redoes ALL of that work, only the
         ~4,000 kernel launches per double-backward are no longer issued from Python.  Worth most when
         the per-rank batch is small and the launches are host-bound (strong scaling at 4-8 GPUs).
         Batches may live in pinned host memory: their H2D copies become nodes of the graph.
-        ``out``: write H v straight into this buffer (e.g. the engine's w) instead of a private one."""
-        return GraphedHVP(self, ws=ws, warmup=warmup, out=out)
+        ``out``: write H v straight into this buffer (e.g. the engine's w) instead of a private one.
+        ``pipeline``: capture the v-independent half (forward + first backward) and the v-dependent half (second
+        backward + gather) as two graphs and start the first half of the NEXT application on a side stream as soon
+        as this one has finished, so it overlaps whatever the caller does between applications (the Lanczos
+        recurrence and its collectives).  Every application still replays both halves; the operator (weights,
+        batches) must not change while a prefetched half is in flight -- call ``invalidate()`` if it does."""
+        return GraphedHVP(self, ws=ws, warmup=warmup, out=out, pipeline=pipeline)
 
 
 class GraphedHVP:
@@ -244,7 +249,8 @@ class GraphedHVP:
     graph is replayed, and the result is copied out (or the graph's output buffer is handed to the
     engine directly when it asks for it via ``out_buffer``)."""
 
-    def __init__(self, op: "HessianVectorProduct", ws=None, warmup: int = 3, out: Optional[torch.Tensor] = None):
+    def __init__(self, op: "HessianVectorProduct", ws=None, warmup: int = 3, out: Optional[torch.Tensor] = None,
+                 pipeline: bool = False):
         from . import kernels
         for b in op.batches:
             t = _first(b)
@@ -265,8 +271,20 @@ class GraphedHVP:
         self.v.normal_()
         self.v /= torch.linalg.vector_norm(self.v)
 
+        self.pipeline = bool(pipeline)
+        self.graph_first = None
+        self._primed = False
+
         def run():
             op.accumulate_into(self.v, self.out, dot_with=self.v, dot_out=self.dot, ws=self.ws, ops=kernels)
+
+        def first_half():                       # forward + first backward of every micro-batch: does not depend on v
+            op._prepare_model()
+            with _math_sdpa():
+                for i in range(len(op.batches)):
+                    op._first_backward(i)
+        if self.pipeline:
+            op.cache_graph = True               # run() then only performs the second backward over the graphs first_half() built
         # A cached first-backward graph must be (re)built on the side stream: autograd replays each node on
         # the stream its forward ran on, and a capture may fork into a side stream but never into the legacy
         # default stream (cudaErrorStreamCaptureInvalidated).
@@ -275,16 +293,55 @@ class GraphedHVP:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), _capturable_scalar_tensors():
             for _ in range(max(1, warmup)):
+                if self.pipeline:
+                    op.clear_cache()
+                    first_half()
                 run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
         before, h2d0 = kernels.launch_count, op.h2d_bytes
-        with torch.cuda.graph(self.graph), _capturable_scalar_tensors():
-            run()
+        if self.pipeline:
+            # two graphs over ONE memory pool: the second backward reads the activations / first-order gradients the
+            # first graph leaves behind; they are always replayed in capture order and never concurrently
+            op.clear_cache()
+            pool = torch.cuda.graph_pool_handle()
+            self.graph_first = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_first, pool=pool), _capturable_scalar_tensors():
+                first_half()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, pool=pool), _capturable_scalar_tensors():
+                run()
+            self.side = torch.cuda.Stream(device=dev)
+            self._ev_first = torch.cuda.Event()
+            self._ev_second = torch.cuda.Event()
+        else:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph), _capturable_scalar_tensors():
+                run()
         self.launches_per_replay = kernels.launch_count - before
         self.h2d_bytes_per_replay = op.h2d_bytes - h2d0     # pinned-host batches: copied by the graph on every replay
         self.applications = 0
+
+    # -- pipelined mode: the v-independent half of the next application runs ahead on a side stream --------------
+    def _launch_first(self, main) -> None:
+        self._ev_second.record(main)                        # everything this application read is finished with
+        self.side.wait_event(self._ev_second)
+        with torch.cuda.stream(self.side):
+            self.graph_first.replay()
+            self._ev_first.record(self.side)
+        self.op.h2d_bytes += self.h2d_bytes_per_replay
+        self._primed = True
+
+    def drain(self) -> None:
+        """Make the current stream wait for a prefetched first half (so a timed region accounts for it)."""
+        if self.pipeline and self._primed:
+            torch.cuda.current_stream(self.op.device).wait_event(self._ev_first)
+
+    def invalidate(self) -> None:
+        """Drop a prefetched first half (call after the model's weights or the batches changed)."""
+        if self.pipeline and self._primed:
+            torch.cuda.current_stream(self.op.device).wait_event(self._ev_first)
+            self._primed = False
 
     @property
     def weights(self):
@@ -297,14 +354,22 @@ class GraphedHVP:
     def accumulate_into(self, v: torch.Tensor, out: torch.Tensor, dot_with=None, dot_out=None,
                         ws=None, ops=None, phases=None) -> None:
         from . import kernels
+        main = torch.cuda.current_stream(self.op.device)
+        if self.pipeline:
+            if not self._primed:
+                self._launch_first(main)
+            main.wait_event(self._ev_first)
+        else:
+            self.op.h2d_bytes += self.h2d_bytes_per_replay
         self.v.copy_(v.reshape(-1))
         self.graph.replay()
         kernels.launch_count += self.launches_per_replay
-        self.op.h2d_bytes += self.h2d_bytes_per_replay
         if out.data_ptr() != self.out.data_ptr():
             out.copy_(self.out)
         if dot_out is not None:
             dot_out.copy_(self.dot)           # dot_with is v itself in the Lanczos loop (alpha = <Hv, v>)
+        if self.pipeline:
+            self._launch_first(main)          # next application's forward + first backward, overlapping the caller's work
         self.applications += 1
 
     def __call__(self, v: torch.Tensor) -> torch.Tensor:

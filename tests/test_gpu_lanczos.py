@@ -287,6 +287,25 @@ def test_cuda_graph_full_double_backward(hlv, cuda_dev, golden_dir):
     assert _rel(graphed.T, eager.T, float(eager.T.abs().max())) < 1e-5
     with pytest.raises(ValueError, match="pinned"):
         hlv.HessianVectorProduct(model, [torch.from_numpy(g["ids"])], device=cuda_dev).capture()
+    # pipelined capture: two graphs, the v-independent half of the next application prefetched on a side stream
+    ids2 = torch.from_numpy(g["ids2"]).to(cuda_dev)
+    for batches in ([ids_host.to(cuda_dev)], [ids_host], [ids_host.to(cuda_dev), ids2]):
+        opp = hlv.HessianVectorProduct(model, batches, device=cuda_dev)
+        ref_op = hlv.HessianVectorProduct(model, [b.to(cuda_dev) for b in batches])
+        pop = opp.capture(pipeline=True)
+        assert pop.graph_first is not None
+        for k in range(3):
+            x = (k + 1) * vec
+            want = ref_op(x)
+            assert _rel(pop(x), want, float(want.abs().max())) < 2e-5
+        pop.drain()
+        pop.invalidate()
+        want = ref_op(vec)
+        assert _rel(pop(vec), want, float(want.abs().max())) < 2e-5
+        piped = hlv.lanczos(pop, 10, vec, reorth="full")
+        eager2 = hlv.lanczos(ref_op, 10, vec, reorth="full")
+        assert _rel(piped.T, eager2.T, float(eager2.T.abs().max())) < 1e-5
+        torch.cuda.synchronize()
 
 
 def test_block_and_per_tensor_operators(hlv, cuda_dev, golden_dir):
