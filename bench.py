@@ -69,9 +69,10 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--blas", default="default", choices=["default", "cublas", "cublaslt"],
                     help="torch.backends.cuda.preferred_blas_library for the HVP's fp32 GEMMs (probe; fp32 either way)")
-    ap.add_argument("--no-pipeline", action="store_true",
-                    help="graph mode: one graph per application instead of two (v-independent half prefetched on a side stream "
-                         "while the recurrence of the previous iteration runs)")
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "on", "off"],
+                    help="graph mode: capture the application as two graphs and prefetch the v-independent half of iteration j+1 on a "
+                         "side stream while the recurrence and collectives of iteration j run.  auto = on for N>1 (+2%% at N=8), off at "
+                         "N=1 (+0.5%% there, and the concurrent GEMMs would blur the per-kernel roofline timings)")
     ap.add_argument("--cache-graph", action="store_true", help="keep the first-backward graph across iterations (extra, not the headline)")
     ap.add_argument("--hvp-mode", default="graph", choices=["graph", "eager"],
                     help="graph: the whole double-backward (forward, both backward passes, gather) is captured once into a CUDA "
@@ -285,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
             hvp_modes[tag] = "eager"
             return op
         try:
-            pipe = not args.no_pipeline
+            pipe = args.pipeline == "on" or (args.pipeline == "auto" and world > 1)
             g = op.capture(out=eng.w if world == 1 else eng.hv_full, pipeline=pipe)
             hvp_modes[tag] = ("cuda_graph (forward + both backward passes + gather replayed every iteration"
                               + ("; the v-independent half of iteration j+1 overlaps the recurrence of iteration j on a side stream)" if pipe else ")"))
