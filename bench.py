@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--no-fused", action="store_true", help="CGS2 as 4 separate passes (project, update, project, update)")
     ap.add_argument("--extras", action="store_true", help="also time the cached-first-backward HVP modes (reported under 'extras'); default at N=1")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--reorth-tol", type=float, default=None,
+                    help="NOT the headline: apply the last Gram-Schmidt pass only when a projection coefficient exceeds tol*|w| "
+                         "(gpytorch's rule, tol=1e-5), decided on the device; default = unconditional two-pass CGS")
     ap.add_argument("--blas", default="default", choices=["default", "cublas", "cublaslt"],
                     help="torch.backends.cuda.preferred_blas_library for the HVP's fp32 GEMMs (probe; fp32 either way)")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "on", "off"],
@@ -250,7 +253,7 @@ def bench_config(args, seq, n):
     return {"workload": "GPT-2 124M (GPT2Config(vocab_size=50257, n_positions=512), random init seed 0, eager attention, fp32, TF32 off) "
                         "Lanczos m=100 with full two-pass classical Gram-Schmidt reorthogonalisation, "
                         f"{'fp32' if args.basis_dtype == 'f32' else 'bf16'} basis" if not args.small else "SMALL functional check (not a benchmark)",
-            "P": n, "global_batch": args.global_batch, "micro_batch": args.micro_batch, "seq_len": seq, "basis_depth": M_DEPTH,
+            "reorth_tol": args.reorth_tol, "P": n, "global_batch": args.global_batch, "micro_batch": args.micro_batch, "seq_len": seq, "basis_depth": M_DEPTH,
             "depth_schedule": "j=0..99 (the m=100 run itself)" if args.steps == M_DEPTH else f"floor((i+0.5)*100/{args.steps}) over a pre-built orthonormal basis",
             "l2": "no flush: every pass streams >= 0.5 GB per basis row, far beyond the 126 MB L2",
             "parallelism": f"{args.gpus} rank(s): micro-batches sharded (reduce-scatter of Hv), basis sharded along P (k-float all-reduce)"}
@@ -297,7 +300,7 @@ def run_ours(args, rank, world, local_rank):
             return op
     basis_dtype = torch.float32 if args.basis_dtype == "f32" else torch.bfloat16
     eng = hlv.LanczosEngine(op_dev, n, M_DEPTH, dev, reorth="full", basis_dtype=basis_dtype, comm=comm, profile=True,
-                            fused_cgs=not args.no_fused)
+                            fused_cgs=not args.no_fused, reorth_tol=args.reorth_tol)
     torch.manual_seed(7)                                  # probe: randn(P)/norm, diego_pythia.py:147-149
     v0 = torch.randn(n)
     v0 = (v0 / v0.norm()).to(dev)
@@ -424,6 +427,8 @@ def run_ours(args, rank, world, local_rank):
             gbs = fn(d) / (d["ms"] * 1e-3) / 1e9
             kernels_out[name] = {"ms_total": round(d["ms"], 3), "launches": d["calls"], "achieved_gbs": round(gbs, 1),
                                  "frac_of_peak": round(gbs / peak, 4), "bytes_per_launch": fn(d) / d["calls"]}
+    if args.reorth_tol is not None and "cgs_update" in kernels_out:
+        kernels_out["cgs_update"]["note"] = "predicated pass: bytes are counted as if every launch ran; skipped launches move none"
     ours_ms = sum(v["ms_total"] for v in kernels_out.values())
     ours_bytes = sum(v["bytes_per_launch"] * v["launches"] for v in kernels_out.values())
     bound_ms = ours_bytes / (peak * 1e9) * 1e3 / args.steps          # per step, this rank's shard, at the measured HBM peak

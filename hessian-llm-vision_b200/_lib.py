@@ -41,6 +41,9 @@ SIGNATURES = {
     "hlv_cgs_project_bf16": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _sz, _vp]),
     "hlv_cgs_update_f32": (C.c_int, [_vp, _i64, _i32, _vp, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
     "hlv_cgs_update_bf16": (C.c_int, [_vp, _i64, _i32, _vp, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "hlv_cgs_needs_pass": (C.c_int, [_vp, _i32, _vp, _f64, _vp, _vp]),
+    "hlv_cgs_update_if_f32": (C.c_int, [_vp, _i64, _i32, _vp, _f32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "hlv_cgs_update_if_bf16": (C.c_int, [_vp, _i64, _i32, _vp, _f32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "hlv_cgs_fused_max_rows": (C.c_int, [_i32]),
     "hlv_cgs_update_project_f32": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "hlv_cgs_update_project_bf16": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),

@@ -165,10 +165,14 @@ cgs_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const float*
 template <typename BT>
 __global__ void __launch_bounds__(kThreads, 2)
 cgs_update_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const double* __restrict__ c, float sign,
-                  float* __restrict__ w, int64_t n, double* partials, unsigned* counter, double* norm2_out) {
+                  float* __restrict__ w, int64_t n, double* partials, unsigned* counter, double* norm2_out,
+                  const int* __restrict__ run_flag) {
     extern __shared__ float s_c[];                      // sign * (float)c[i]
     __shared__ double s_warp[kWarps];
     const int tid = threadIdx.x;
+    // device-side predication: a pass that an earlier kernel found unnecessary costs one launch and no traffic;
+    // w and norm2_out are left untouched and the ticket counter is not taken (every CTA leaves here)
+    if (run_flag != nullptr && *run_flag == 0) return;
     constexpr int kRowBatch = row_batch<BT>();
     for (int i = tid; i < rows; i += kThreads) s_c[i] = sign * (float)c[i];
     __syncthreads();
@@ -209,6 +213,21 @@ cgs_update_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const double*
         if (tid == 0) partials[blockIdx.x] = t;
         finalize_rows(partials, counter, 1, norm2_out);
     }
+}
+
+// flag = 1 if another Gram-Schmidt pass is needed: some |c[i]| > tol * |w|  (gpytorch's "while any q_i . r > tol",
+// SURVEY Appendix B, with r normalised); NaNs ask for the pass.  One CTA; rows <= HLV_MAX_ROWS.
+__global__ void cgs_needs_pass_kernel(const double* __restrict__ c, int rows, const double* __restrict__ norm2, double tol,
+                                      int* flag) {
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    const double lim = tol * sqrt(norm2[0]);
+    int any = 0;
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) any |= !(fabs(c[i]) <= lim);
+    if (any) atomicOr(&s_any, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) flag[0] = s_any;
 }
 
 // coef[i] = (1/eig[i] - 1/(eig[i]+delta)) * dots[i]   (vector_adjust.cu:11, fp32 like the reference)
@@ -314,7 +333,8 @@ static int project(const char* name, const BT* V, int64_t ldv, int rows, const f
 
 template <typename BT>
 static int update(const char* name, const BT* V, int64_t ldv, int rows, const double* c, float sign, float* w,
-                  int64_t n, double* norm2_out, void* ws_raw, size_t ws_bytes, cudaStream_t stream) {
+                  int64_t n, double* norm2_out, void* ws_raw, size_t ws_bytes, cudaStream_t stream,
+                  const int* run_flag = nullptr) {
     int rc = check_basis(name, V, ldv, rows, w, n);
     if (rc != HLV_OK) return rc;
     HLV_REQUIRE(c != nullptr, HLV_ERR_ARG, "%s: c is NULL", name);
@@ -323,7 +343,7 @@ static int update(const char* name, const BT* V, int64_t ldv, int rows, const do
         HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, 1, &ws), HLV_ERR_WORKSPACE, "%s: workspace too small", name);
     const int grid = persistent_grid((n + kTile - 1) / kTile, resident_ctas(cgs_update_kernel<BT>, rows * sizeof(float)));
     cgs_update_kernel<BT><<<grid, kThreads, rows * sizeof(float), stream>>>(V, ldv, rows, c, sign, w, n, ws.partials,
-                                                                           ws.counters, norm2_out);
+                                                                           ws.counters, norm2_out, run_flag);
     HLV_LAUNCH_CHECK(name);
     return HLV_OK;
 }
@@ -368,6 +388,21 @@ int hlv_cgs_update_f32(const float* V, int64_t ldv, int rows, const double* c, f
 int hlv_cgs_update_bf16(const uint16_t* V, int64_t ldv, int rows, const double* c, float sign, float* w, int64_t n,
                         double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
     return update<uint16_t>("hlv_cgs_update_bf16", V, ldv, rows, c, sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int hlv_cgs_update_if_f32(const float* V, int64_t ldv, int rows, const double* c, float sign, float* w, int64_t n,
+                          double* norm2_out, const int* run_flag, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return update<float>("hlv_cgs_update_if_f32", V, ldv, rows, c, sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream), run_flag);
+}
+int hlv_cgs_update_if_bf16(const uint16_t* V, int64_t ldv, int rows, const double* c, float sign, float* w, int64_t n,
+                           double* norm2_out, const int* run_flag, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return update<uint16_t>("hlv_cgs_update_if_bf16", V, ldv, rows, c, sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream), run_flag);
+}
+int hlv_cgs_needs_pass(const double* c, int rows, const double* norm2, double tol, int* flag_out, hlv_stream_t stream) {
+    HLV_REQUIRE(c && norm2 && flag_out && rows >= 1 && tol >= 0.0, HLV_ERR_ARG, "hlv_cgs_needs_pass: bad argument");
+    cgs_needs_pass_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(c, rows, norm2, tol, flag_out);
+    HLV_LAUNCH_CHECK("hlv_cgs_needs_pass");
+    return HLV_OK;
 }
 
 int hlv_vector_adjust_f32(const float* grad_vector, const float* V, const float* eigvals,

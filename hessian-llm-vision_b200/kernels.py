@@ -184,15 +184,32 @@ def cgs_project(V: torch.Tensor, rows: int, w: torch.Tensor, c_out: torch.Tensor
 
 
 def cgs_update(V: torch.Tensor, rows: int, c: torch.Tensor, w: torch.Tensor,
-               norm2_out: Optional[torch.Tensor], ws: Workspace, sign: float = -1.0) -> None:
-    """w += sign * V[:rows, :n]^T c ; norm2_out = sum w^2."""
+               norm2_out: Optional[torch.Tensor], ws: Workspace, sign: float = -1.0,
+               run_flag: Optional[torch.Tensor] = None) -> None:
+    """w += sign * V[:rows, :n]^T c ; norm2_out = sum w^2.  With ``run_flag`` (device int32[1]) the pass is
+    predicated on the device: flag 0 = leave w and norm2_out untouched (no host round trip)."""
     global launch_count
     n = w.numel()
     p, ldv, sfx = _basis(V, rows, n, "cgs_update")
     with torch.cuda.device(w.device):
-        _lib.call(f"hlv_cgs_update_{sfx}", p, ldv, int(rows), _cuda(c, torch.float64, "c"), float(sign),
-                  _cuda(w, torch.float32, "w"), n, _opt(norm2_out, torch.float64, "norm2_out"),
-                  ws.ptr, ws.nbytes, _stream())
+        if run_flag is None:
+            _lib.call(f"hlv_cgs_update_{sfx}", p, ldv, int(rows), _cuda(c, torch.float64, "c"), float(sign),
+                      _cuda(w, torch.float32, "w"), n, _opt(norm2_out, torch.float64, "norm2_out"),
+                      ws.ptr, ws.nbytes, _stream())
+        else:
+            _lib.call(f"hlv_cgs_update_if_{sfx}", p, ldv, int(rows), _cuda(c, torch.float64, "c"), float(sign),
+                      _cuda(w, torch.float32, "w"), n, _opt(norm2_out, torch.float64, "norm2_out"),
+                      _cuda(run_flag, torch.int32, "run_flag"), ws.ptr, ws.nbytes, _stream())
+    launch_count += 1
+
+
+def cgs_needs_pass(c: torch.Tensor, rows: int, norm2: torch.Tensor, tol: float, flag_out: torch.Tensor) -> None:
+    """flag_out[0] = 1 if some |c[i]| > tol * sqrt(norm2[0]) (another Gram-Schmidt pass is needed), else 0 --
+    gpytorch's "while any q_i . r > tol" test, evaluated on the device."""
+    global launch_count
+    with torch.cuda.device(c.device):
+        _lib.call("hlv_cgs_needs_pass", _cuda(c, torch.float64, "c"), int(rows), _cuda(norm2, torch.float64, "norm2"),
+                  float(tol), _cuda(flag_out, torch.int32, "flag_out"), _stream())
     launch_count += 1
 
 

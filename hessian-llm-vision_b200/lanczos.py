@@ -183,7 +183,8 @@ class LanczosEngine:
     def __init__(self, hvp: Callable, n: int, n_iter: int, device, reorth: Optional[str] = None,
                  basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
                  breakdown_tol: Optional[float] = None, comm: Optional[Comm] = None, ops=None,
-                 profile: bool = False, column_vectors: bool = False, cgs_passes: int = 2, fused_cgs: bool = True):
+                 profile: bool = False, column_vectors: bool = False, cgs_passes: int = 2, fused_cgs: bool = True,
+                 reorth_tol: Optional[float] = None):
         if reorth not in (None, "full"):
             raise ValueError("reorth must be None or 'full'")
         if basis_dtype not in (torch.float32, torch.bfloat16):
@@ -242,6 +243,16 @@ class LanczosEngine:
                       and sn < 2 ** 31 - 4096)            # the fused pass addresses tiles with 32-bit TMA coordinates
         self.fused_max_rows = ops.fused_max_rows(basis_dtype) if self.fused else 0
         self.fused_min_rows = 1 if fused_cgs == "force" else 4
+        # reorth_tol (None = unconditional two-pass CGS, the default): the last pass of CGS2 is applied only when the
+        # projection of the once-orthogonalised w still has a component > reorth_tol * |w| -- gpytorch's
+        # "re-orthogonalise while any q_i . r > tol" (tol = 1e-5 there).  The test and the predication live on the
+        # device (hlv_cgs_needs_pass, hlv_cgs_update_if_*): no host round trip, and a skipped pass costs no traffic.
+        self.reorth_tol = None if reorth_tol is None else float(reorth_tol)
+        if self.reorth_tol is not None:
+            if not (self.fused and self.cgs_passes == 2):
+                raise ValueError("reorth_tol needs the fused two-pass Gram-Schmidt path (reorth='full', cgs_passes=2, fused_cgs on)")
+            self.pass_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.norm2_b = torch.zeros(1, **f64)
         self.j = 0
         self.launches = 0
 
@@ -342,6 +353,7 @@ class LanczosEngine:
             ops.lanczos_update(self.w, v_j, self._v_shard(j - 1), self.alphas[j: j + 1],
                                self.betas[j: j + 1], self.norm2, self.ws)
         ph.stop("update")
+        norm_reduced = False
         if self.reorth == "full":
             rows = j + 1
             fused = self.fused and self.fused_min_rows <= rows <= self.fused_max_rows
@@ -364,10 +376,23 @@ class LanczosEngine:
                     ph.stop("cgs_project", rows)
                 comm.all_reduce_sum(nxt_c[:rows])
                 cur, nxt_c = nxt_c, cur
-            ph.start("cgs_update")
-            ops.cgs_update(self.basis, rows, cur, self.w, self.norm2, self.ws)
-            ph.stop("cgs_update", rows)
-        comm.all_reduce_sum(self.norm2)
+            if self.reorth_tol is not None and fused:
+                # cur = V w' and norm2 = |w'|^2 were measured by the fused pass: is w' orthogonal enough already?
+                comm.all_reduce_sum(self.norm2)
+                ops.cgs_needs_pass(cur, rows, self.norm2, self.reorth_tol, self.pass_flag)
+                self.norm2_b.zero_()
+                ph.start("cgs_update")
+                ops.cgs_update(self.basis, rows, cur, self.w, self.norm2_b, self.ws, run_flag=self.pass_flag)
+                ph.stop("cgs_update", rows)
+                comm.all_reduce_sum(self.norm2_b)
+                self.norm2.copy_(torch.where(self.pass_flag != 0, self.norm2_b, self.norm2))
+                norm_reduced = True
+            else:
+                ph.start("cgs_update")
+                ops.cgs_update(self.basis, rows, cur, self.w, self.norm2, self.ws)
+                ph.stop("cgs_update", rows)
+        if not norm_reduced:
+            comm.all_reduce_sum(self.norm2)
         if store_next:
             ph.start("normalize")
             nxt = j + 1
@@ -450,7 +475,8 @@ def lanczos(hvp: Callable, n_iter: int, v0: torch.Tensor, reorth: Optional[str] 
             basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
             breakdown_tol: Optional[float] = None, check_every: int = 16, normalize_v0: bool = False,
             comm: Optional[Comm] = None, ops=None, profile: bool = False, column_vectors: bool = False,
-            on_iteration: Optional[Callable[[int, LanczosEngine], None]] = None, fused_cgs: bool = True) -> LanczosResult:
+            on_iteration: Optional[Callable[[int, LanczosEngine], None]] = None, fused_cgs: bool = True,
+            reorth_tol: Optional[float] = None) -> LanczosResult:
     """Run ``n_iter`` Lanczos iterations of the symmetric operator ``hvp`` from ``v0``.
 
     hvp: callable v[P] -> Hv.  It may return a flat [P] (or [P,1]) tensor, or -- to use the fused
@@ -459,6 +485,9 @@ def lanczos(hvp: Callable, n_iter: int, v0: torch.Tensor, reorth: Optional[str] 
          (``hvp.HessianVectorProduct``).
     reorth: None = the reference hand loop (lanczostrain_hand.py:171-203);
             'full' = hand-loop order + two-pass classical Gram-Schmidt against all stored rows.
+    reorth_tol: None = both passes always; a float = apply the second pass's update only when some projection
+            coefficient of the once-orthogonalised w exceeds reorth_tol * |w| (gpytorch's rule with tol=1e-5),
+            decided and predicated on the device.
     v0 must have unit norm (pass normalize_v0=True otherwise), as in the reference.
     """
     dev = v0.device
@@ -466,7 +495,7 @@ def lanczos(hvp: Callable, n_iter: int, v0: torch.Tensor, reorth: Optional[str] 
         raise RuntimeError("lanczos: v0 must live on a CUDA device; this engine has no CPU path")
     eng = LanczosEngine(hvp, v0.numel(), n_iter, dev, reorth=reorth, basis_dtype=basis_dtype,
                         keep_basis=keep_basis, breakdown_tol=breakdown_tol, comm=comm, ops=ops,
-                        profile=profile, column_vectors=column_vectors, fused_cgs=fused_cgs)
+                        profile=profile, column_vectors=column_vectors, fused_cgs=fused_cgs, reorth_tol=reorth_tol)
     eng.start(v0, normalize=normalize_v0)
     for j in range(n_iter):
         eng.step(j)

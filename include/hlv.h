@@ -118,6 +118,19 @@ int hlv_cgs_update_bf16(const uint16_t* V, int64_t ldv, int rows, const double* 
                         float* w, int64_t n, double* norm2_out,
                         void* ws, size_t ws_bytes, hlv_stream_t stream);
 
+/* Conditional re-orthogonalisation without a host round trip (gpytorch's lanczos_tridiag re-orthogonalises "while any
+ * q_i . r > tol", called at gpt2_hessian_cpu.py:207-213).  hlv_cgs_needs_pass sets flag_out[0] = 1
+ * when some |c[i]| > tol * sqrt(norm2[0]) (c = the coefficients a projection just measured, norm2 = |w|^2), else 0;
+ * hlv_cgs_update_if_* is hlv_cgs_update_* that returns at once -- w and norm2_out untouched -- when run_flag[0] == 0
+ * (run_flag NULL: always runs).  Everything stays on the device and in stream order (CUDA-graph safe). */
+int hlv_cgs_needs_pass(const double* c, int rows, const double* norm2, double tol, int* flag_out, hlv_stream_t stream);
+int hlv_cgs_update_if_f32 (const float*    V, int64_t ldv, int rows, const double* c, float sign,
+                           float* w, int64_t n, double* norm2_out, const int* run_flag,
+                           void* ws, size_t ws_bytes, hlv_stream_t stream);
+int hlv_cgs_update_if_bf16(const uint16_t* V, int64_t ldv, int rows, const double* c, float sign,
+                           float* w, int64_t n, double* norm2_out, const int* run_flag,
+                           void* ws, size_t ws_bytes, hlv_stream_t stream);
+
 /* Fused middle pass of two-pass Gram-Schmidt: w -= V^T c_in ; c_out = V w_new ; norm2_out = |w_new|^2,
  * reading V from HBM once (a [rows x tile] slab is staged in shared memory by 2-D tiled TMA boxes of
  * [8 rows x 256 columns] and used for both the update and the projection).  CGS2 = project,

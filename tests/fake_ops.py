@@ -67,7 +67,13 @@ def cgs_project(V, rows, w, c_out, ws):
     c_out[:rows] = V[:rows, : w.numel()].double() @ w.double()
 
 
-def cgs_update(V, rows, c, w, norm2_out, ws, sign=-1.0):
+def cgs_needs_pass(c, rows, norm2, tol, flag_out):
+    flag_out[0] = int(bool((c[:rows].abs() > tol * torch.sqrt(norm2[0])).any()))
+
+
+def cgs_update(V, rows, c, w, norm2_out, ws, sign=-1.0, run_flag=None):
+    if run_flag is not None and int(run_flag[0]) == 0:
+        return
     w += sign * (V[:rows, : w.numel()].float().t() @ c[:rows].float())
     if norm2_out is not None:
         norm2_out[0] = torch.dot(w.double(), w.double())

@@ -310,3 +310,26 @@ def test_lm_loss_disables_kv_cache_without_changing_the_loss():
                                        attn_implementation="eager")).eval()
     ids = torch.randint(0, 61, (2, 16))
     assert torch.equal(hvp.lm_loss(model, ids), model(input_ids=ids, labels=ids).loss)
+
+
+def test_conditional_second_pass_host_logic():
+    """reorth_tol: the second Gram-Schmidt pass's update is predicated on a device flag (gpytorch's "while any
+    q_i . r > tol").  tol=0 always applies it (== unconditional CGS2), a huge tol never does; a sensible tol keeps
+    T and orthogonality at working precision.  Host logic only (test double on CPU)."""
+    import hessian_llm_vision_b200 as hlv
+    M, v0 = _sym(11, 400)
+    m = 30
+    run = lambda **kw: hlv.lanczos(lambda v: M @ v, m, v0, reorth="full", ops=fake_ops, **kw)
+    base = run()
+    scale = float(base.T.abs().max())
+    always = run(reorth_tol=0.0)
+    assert torch.equal(always.T, base.T) and torch.equal(always.Q, base.Q)
+    never = run(reorth_tol=1e30)
+    cond = run(reorth_tol=1e-5)
+    for r in (never, cond):
+        assert float((r.T - base.T).abs().max()) / scale < 2e-5
+        G = r.Q.double() @ r.Q.double().t()
+        assert float((G - torch.eye(m, dtype=torch.float64)).abs().max()) < 1e-4
+    assert float((cond.Q - base.Q).abs().max()) < 1e-4
+    with pytest.raises(ValueError, match="reorth_tol"):
+        run(reorth_tol=1e-5, fused_cgs=False)

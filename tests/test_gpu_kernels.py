@@ -346,3 +346,40 @@ def test_adjust_implicit_equals_explicit_ritz_vectors(K, cuda_dev, dtype, m, k, 
     Va = (Y.t() @ Q[:, :n].double()).float()
     ref_all = oracle.lowrank_adjust(grad.cpu(), Va.cpu(), lam.float().cpu(), delta)
     assert float((out.cpu() - ref_all).abs().max()) <= 2e-5 * float(ref_all.abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conditional_update_device_predicate(K, cuda_dev, dtype):
+    """hlv_cgs_needs_pass / hlv_cgs_update_if_*: the test and the predication happen on the device."""
+    rows, n = 20, 70_003
+    V, w = _basis(rows, n, cuda_dev, dtype, 77)
+    ws = _ws(K, cuda_dev, rows)
+    nrm = torch.tensor([4.0], dtype=torch.float64, device=cuda_dev)              # |w| = 2
+    flag = torch.full((1,), 7, dtype=torch.int32, device=cuda_dev)
+    c = torch.full((rows,), 1e-6, dtype=torch.float64, device=cuda_dev)
+    K.cgs_needs_pass(c, rows, nrm, 1e-5, flag)
+    assert int(flag.item()) == 0                                                 # every |c_i| <= 1e-5 * 2
+    c[13] = -3e-5
+    K.cgs_needs_pass(c, rows, nrm, 1e-5, flag)
+    assert int(flag.item()) == 1
+    K.cgs_needs_pass(c, 13, nrm, 1e-5, flag)                                     # the large one is outside the first 13 rows
+    assert int(flag.item()) == 0
+    c[2] = float("nan")
+    K.cgs_needs_pass(c, rows, nrm, 1e30, flag)
+    assert int(flag.item()) == 1                                                 # NaN asks for the pass
+    # predicated update: flag 0 leaves w and norm2 untouched, flag 1 is the plain update
+    c = torch.randn(rows, dtype=torch.float64, device=cuda_dev)
+    w0, n0 = w.clone(), torch.tensor([123.0], dtype=torch.float64, device=cuda_dev)
+    flag.zero_()
+    K.cgs_update(V, rows, c, w, n0, ws, run_flag=flag)
+    assert torch.equal(w, w0) and n0.item() == 123.0
+    flag.fill_(1)
+    K.cgs_update(V, rows, c, w, n0, ws, run_flag=flag)
+    w_ref = w0.clone()
+    n_ref = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+    K.cgs_update(V, rows, c, w_ref, n_ref, ws)
+    assert torch.equal(w, w_ref) and n0.item() == n_ref.item()
+    flag.zero_()                                                                 # and the workspace ticket is still usable
+    K.cgs_update(V, rows, c, w, n0, ws, run_flag=flag)
+    K.cgs_update(V, rows, c, w, n0, ws)
+    assert n0.item() == float(w.double() @ w.double()) or abs(n0.item() - float(w.double() @ w.double())) <= 1e-5 * n0.item()

@@ -139,6 +139,29 @@ def test_fused_and_unfused_cgs2_agree(hlv, cuda_dev):
     assert _rel(c.T, e.T, scale) < 1e-4
 
 
+def test_conditional_second_pass(hlv, cuda_dev):
+    """reorth_tol (gpytorch's "while any q_i . r > tol", decided on the device): tol=0 reproduces unconditional CGS2
+    bit for bit; tol=1e-5 keeps T within the per-iteration bar and the basis orthogonal to working precision."""
+    n, m = 70_003, 60
+    torch.manual_seed(5)
+    d = (torch.randn(n) * 2).to(cuda_dev)
+    v0 = hlv.probe_vector(n, 3, cuda_dev)
+    op = lambda q: d * q
+    base = hlv.lanczos(op, m, v0, reorth="full")
+    scale = float(base.T.abs().max())
+    always = hlv.lanczos(op, m, v0, reorth="full", reorth_tol=0.0)
+    assert torch.equal(always.T, base.T) and torch.equal(always.Q, base.Q)
+    cond = hlv.lanczos(op, m, v0, reorth="full", reorth_tol=1e-5)
+    assert _rel(cond.T, base.T, scale) < 1e-5
+    Q = cond.Q.double()
+    assert float((Q @ Q.t() - torch.eye(m, dtype=torch.float64, device=cuda_dev)).abs().max()) < 2e-5
+    ref = oracle.lanczos_cgs2(lambda v: d.cpu() * v, v0.cpu(), m, reorth="full")
+    ev_ref = torch.linalg.eigvalsh(ref["T"].double())
+    assert _rel(cond.eigvals, ev_ref, float(ev_ref.abs().max())) < 1e-4
+    with pytest.raises(ValueError, match="reorth_tol"):
+        hlv.lanczos(op, m, v0, reorth="full", reorth_tol=1e-5, fused_cgs=False)
+
+
 def test_bf16_basis_vs_bf16_oracle(hlv, cuda_dev):
     M, v0 = _sym(9, 2000)
     Md = M.to(cuda_dev)
