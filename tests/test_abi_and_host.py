@@ -196,8 +196,9 @@ for r in range(world):
     A = torch.randn(n, n); Ms.append((A + A.t()) / 2)
 v = torch.randn(n); v0 = v / v.norm()
 mine = Ms[rank] / world
+tol = os.environ.get("HLV_REORTH_TOL", "")
 res = hlv.lanczos(lambda x: mine @ x, m, v0, reorth=os.environ["HLV_REORTH"] or None, ops=fake_ops,
-                  comm=hlv.Comm(), keep_basis=True)
+                  comm=hlv.Comm(), keep_basis=True, reorth_tol=float(tol) if tol else None)
 if rank == 0:
     torch.save({"T": res.T, "n_local": res.n_local, "m": res.m}, os.environ["HLV_OUT"])
 dist.barrier()
@@ -205,8 +206,8 @@ dist.destroy_process_group()
 """
 
 
-@pytest.mark.parametrize("reorth,n", [("full", 100), ("", 64)])
-def test_sharded_engine_two_ranks_gloo(tmp_path, reorth, n):
+@pytest.mark.parametrize("reorth,n,tol", [("full", 100, ""), ("", 64, ""), ("full", 100, "1e-5"), ("full", 100, "0")])
+def test_sharded_engine_two_ranks_gloo(tmp_path, reorth, n, tol):
     import socket
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     script = tmp_path / "worker.py"
@@ -215,7 +216,7 @@ def test_sharded_engine_two_ranks_gloo(tmp_path, reorth, n):
     procs = []
     for r in range(2):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", HLV_ROOT=ROOT, HLV_PORT=str(port), HLV_N=str(n),
-                   HLV_REORTH=reorth, HLV_OUT=str(out), OMP_NUM_THREADS="1")
+                   HLV_REORTH=reorth, HLV_REORTH_TOL=tol, HLV_OUT=str(out), OMP_NUM_THREADS="1")
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     for p in procs:
         o, _ = p.communicate(timeout=300)
