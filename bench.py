@@ -303,7 +303,8 @@ def run_ours(args, rank, world, local_rank):
                             fused_cgs=not args.no_fused, reorth_tol=args.reorth_tol)
     torch.manual_seed(7)                                  # probe: randn(P)/norm, diego_pythia.py:147-149
     v0 = torch.randn(n)
-    v0 = (v0 / v0.norm()).to(dev)
+    v0 = v0.to(dev)                                       # normalise ON THE DEVICE: torch's CPU float32 norm of 1.24e8 elements
+    v0 /= torch.linalg.vector_norm(v0.double()).float()   # is 1.4% off (profiles/README.md), which would leave |v0|^2 - 1 = 2.7e-2
     sched = depth_schedule(args.steps)
     real_run = args.steps == M_DEPTH
 
