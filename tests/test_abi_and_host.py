@@ -334,3 +334,16 @@ def test_conditional_second_pass_host_logic():
     assert float((cond.Q - base.Q).abs().max()) < 1e-4
     with pytest.raises(ValueError, match="reorth_tol"):
         run(reorth_tol=1e-5, fused_cgs=False)
+
+
+def test_bench_and_scripts_parse():
+    """bench.py / scripts are only exercised on the GPU box; catch syntax and argparse slips on CPU."""
+    import py_compile
+    for fn in ["bench.py", "__graft_entry__.py"] + [os.path.join("scripts", f) for f in os.listdir(os.path.join(ROOT, "scripts")) if f.endswith(".py")]:
+        py_compile.compile(os.path.join(ROOT, fn), doraise=True)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0
+    text = r.stdout + r.stderr                       # bench points fd 1 at stderr: only the JSON line may reach stdout
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--hvp-mode", "--pipeline", "--reorth-tol"):
+        assert flag in text
+    assert r.stdout == ""
