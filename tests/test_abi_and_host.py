@@ -347,3 +347,48 @@ def test_bench_and_scripts_parse():
     for flag in ("--gpus", "--steps", "--warmup", "--impl", "--hvp-mode", "--pipeline", "--reorth-tol"):
         assert flag in text
     assert r.stdout == ""
+
+
+_REPLICA_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["HLV_ROOT"])
+import hessian_llm_vision_b200 as hlv
+from tests import fake_ops
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["HLV_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+torch.manual_seed(2)
+A = torch.randn(150, 150); M = (A + A.t()) / 2
+r = hlv.slq(lambda v: M @ v, 150, 12, seeds=[3, 4, 5, 6, 7], device="cpu", ops=fake_ops, replicas=hlv.Comm())
+if dist.get_rank() == 0:
+    torch.save({"seeds": r.seeds, "eigvals": r.eigvals, "gammas": r.gammas}, os.environ["HLV_OUT"])
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_slq_probes_dealt_over_two_ranks_gloo(tmp_path):
+    """Config 5's multi-GPU shape: probes are independent units, dealt round-robin over the ranks with NO data-path
+    collective ("replicas only"); the (eigvals, gammas) pairs are exchanged once at the end and equal a
+    single-process run probe for probe."""
+    import socket
+    import hessian_llm_vision_b200 as hlv
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_REPLICA_WORKER)
+    out = tmp_path / "res.pt"
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", HLV_ROOT=ROOT, HLV_PORT=str(port), HLV_OUT=str(out), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        o, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, o.decode()[-2000:]
+    got = torch.load(out)
+    torch.manual_seed(2)
+    A = torch.randn(150, 150); M = (A + A.t()) / 2
+    one = hlv.slq(lambda v: M @ v, 150, 12, seeds=[3, 4, 5, 6, 7], device="cpu", ops=fake_ops)
+    assert got["seeds"] == one.seeds == [3, 4, 5, 6, 7]
+    for a, b in zip(got["eigvals"], one.eigvals):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())     # OMP_NUM_THREADS differs between the two runs
+    for a, b in zip(got["gammas"], one.gammas):
+        assert float((a - b).abs().max()) <= 1e-4
