@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhlv.so")
 
 HLV_OK = 0
+HLV_VERSION = 100          # must equal include/hlv.h's HLV_VERSION: a stale libhlv.so is refused at load
 HLV_MAX_ROWS = 1024
 
 
@@ -65,6 +66,9 @@ def load() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args
+        if lib.hlv_version() != HLV_VERSION:
+            raise ImportError(f"{LIB_PATH} is version {lib.hlv_version()}, this package needs {HLV_VERSION}: rebuild it "
+                              "(python __graft_entry__.py --force)")
         _lib = lib
     return _lib
 

@@ -109,14 +109,20 @@ class HessianVectorProduct:
     the GLOBAL number of sequences so that the sum over ranks is the global mean.
 
     per_tensor=True gives the block-diagonal-by-tensor operator of gpt2_savehessian_layer.py.
-    cache_graph=True keeps each micro-batch's first-backward graph alive across applications so
-    an application costs only the second backward (memory for speed; the reference rebuilds it).
+
+    cache_graph: the forward pass and the first backward (gpt2_hessian_cpu.py:94-102) do not depend on v, so
+    their autograd graph can be built ONCE per operator and every application then costs only the second
+    backward (the reference rebuilds it every time).  The result is bit-identical (same kernels on the same
+    saved tensors; tests/test_gpu_zz_full_size.py).  ``"auto"`` (default) keeps a micro-batch's graph when the
+    device has room for it and for the second backward's temporaries, ``True`` always, ``False`` never.  A
+    cached graph is valid while the model's weights and the batches do not change: build a new operator per
+    spectrum run (as the reference scripts do) or call ``clear_cache()``.
     """
 
     def __init__(self, model: torch.nn.Module, batches: Iterable, loss_fn: Callable = lm_loss,
                  params: Optional[Sequence[torch.nn.Parameter]] = None,
                  weights: Optional[Sequence[float]] = None, total_sequences: Optional[int] = None,
-                 per_tensor: bool = False, bn_train_mode: bool = False, cache_graph: bool = False,
+                 per_tensor: bool = False, bn_train_mode: bool = False, cache_graph="auto",
                  device: Optional[torch.device] = None):
         self.model = model
         self.params = list(model.parameters()) if params is None else list(params)
@@ -136,8 +142,12 @@ class HessianVectorProduct:
         self.loss_fn = loss_fn
         self.per_tensor = per_tensor
         self.bn_train_mode = bn_train_mode
+        if cache_graph not in (True, False, "auto"):
+            raise ValueError("cache_graph must be True, False or 'auto'")
         self.cache_graph = cache_graph
         self._graphs = {}
+        self.cached_bytes = 0                       # device memory held by the kept first-backward graphs
+        self.first_backward_builds = 0
         self.applications = 0
         self.h2d_bytes = 0
 
@@ -167,11 +177,26 @@ class HessianVectorProduct:
                                   (batch.values() if isinstance(batch, dict) else (batch if isinstance(batch, (tuple, list)) else [batch]))
                                   if torch.is_tensor(t))
             batch = _to_device(batch, self.device)
+        on_cuda = self.device.type == "cuda"
+        before = torch.cuda.memory_allocated(self.device) if on_cuda and self.cache_graph else 0
         loss = self.loss_fn(self.model, batch) * self.weights[i]
         grads = torch.autograd.grad(loss, self.params, create_graph=True, allow_unused=True)
+        self.first_backward_builds += 1
+        if self.cache_graph == "auto":              # decided once, on the first graph built
+            self.cache_graph = self._room_to_keep(torch.cuda.memory_allocated(self.device) - before) if on_cuda else True
         if self.cache_graph:
             self._graphs[i] = grads
+            if on_cuda:
+                self.cached_bytes += torch.cuda.memory_allocated(self.device) - before
         return grads
+
+    def _room_to_keep(self, graph_bytes: int) -> bool:
+        """Keep the first-backward graphs only if every micro-batch's graph plus the second backward's temporaries
+        (about as large as one graph again) fit in what the device has left."""
+        free, _ = torch.cuda.mem_get_info(self.device)
+        free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        remaining = len(self.batches) - 1
+        return free >= (remaining + 1.5) * max(graph_bytes, 0)
 
     def pieces(self, v: torch.Tensor, i: int) -> List[torch.Tensor]:
         """Per-parameter pieces of (weights[i] * H_i) v for micro-batch i."""
@@ -179,7 +204,7 @@ class HessianVectorProduct:
         self._prepare_model()
         with _math_sdpa():
             grads = self._first_backward(i)
-            keep = self.cache_graph
+            keep = i in self._graphs
             if not self.per_tensor:
                 used = [(g, p, x) for g, p, x in zip(grads, self.params, views) if g is not None and g.requires_grad]
                 hv = torch.autograd.grad([g for g, _, _ in used], [p for _, p, _ in used],
@@ -224,33 +249,38 @@ class HessianVectorProduct:
         return out.unsqueeze(1) if col else out
 
     def clear_cache(self) -> None:
+        """Drop the kept first-backward graphs (after the model's weights or the batches changed)."""
         self._graphs.clear()
+        self.cached_bytes = 0
 
-    def capture(self, ws=None, warmup: int = 3, out: Optional[torch.Tensor] = None, pipeline: bool = False) -> "GraphedHVP":
-        """Capture one full application (every micro-batch's forward, both backward passes and the
-        libhlv gather + fused <Hv, v>) into a CUDA graph; a replay redoes ALL of that work, only the
-        ~4,000 kernel launches per double-backward are no longer issued from Python.  Worth most when
-        the per-rank batch is small and the launches are host-bound (strong scaling at 4-8 GPUs).
+    def capture(self, ws=None, warmup: int = 3, out: Optional[torch.Tensor] = None, pipeline: bool = False,
+                reuse_first: Optional[bool] = None) -> "GraphedHVP":
+        """Capture the application into CUDA graphs: none of the ~4,000 kernel launches per double-backward is
+        issued from Python any more (worth most when the per-rank batch is small and the launches are host-bound).
         Batches may live in pinned host memory: their H2D copies become nodes of the graph.
-        ``out``: write H v straight into this buffer (e.g. the engine's w) instead of a private one.
-        ``pipeline``: capture the v-independent half (forward + first backward) and the v-dependent half (second
-        backward + gather) as two graphs and start the first half of the NEXT application on a side stream as soon
-        as this one has finished, so it overlaps whatever the caller does between applications (the Lanczos
-        recurrence and its collectives).  Every application still replays both halves; the operator (weights,
-        batches) must not change while a prefetched half is in flight -- call ``invalidate()`` if it does."""
-        return GraphedHVP(self, ws=ws, warmup=warmup, out=out, pipeline=pipeline)
+
+        Two graphs over one memory pool: the v-independent half (every micro-batch's forward + first backward) and
+        the v-dependent half (second backward + libhlv gather + fused <Hv, v>).
+        ``reuse_first`` (default: the operator's ``cache_graph`` setting): the first half is replayed ONCE -- at the
+        first application and again after ``invalidate()`` -- and every application replays only the second half.
+        ``reuse_first=False`` redoes ALL of the work on every application, like the reference; with
+        ``pipeline=True`` the first half of the NEXT application is then started on a side stream as soon as this
+        one has finished, so it overlaps whatever the caller does in between (the Lanczos recurrence and its
+        collectives).  The operator (weights, batches) must not change while a graph's first half is live -- call
+        ``invalidate()`` if it does.
+        ``out``: write H v straight into this buffer (e.g. the engine's w) instead of a private one."""
+        return GraphedHVP(self, ws=ws, warmup=warmup, out=out, pipeline=pipeline, reuse_first=reuse_first)
 
 
 class GraphedHVP:
-    """A HessianVectorProduct application replayed from a CUDA graph.
+    """A HessianVectorProduct application replayed from CUDA graphs.
 
     Static buffers: ``v`` (input, length n), ``out`` (H v, length n) and ``dot`` (<Hv, v>).  The
     engine passes its own vector; it is copied into the static input (one 4n-byte D2D copy), the
-    graph is replayed, and the result is copied out (or the graph's output buffer is handed to the
-    engine directly when it asks for it via ``out_buffer``)."""
+    graph is replayed, and the result is copied out (or lands in the caller's buffer given as ``out``)."""
 
     def __init__(self, op: "HessianVectorProduct", ws=None, warmup: int = 3, out: Optional[torch.Tensor] = None,
-                 pipeline: bool = False):
+                 pipeline: bool = False, reuse_first: Optional[bool] = None):
         from . import kernels
         for b in op.batches:
             t = _first(b)
@@ -271,9 +301,16 @@ class GraphedHVP:
         self.v.normal_()
         self.v /= torch.linalg.vector_norm(self.v)
 
+        if reuse_first is None:
+            reuse_first = op.cache_graph is not False and not pipeline
+        if reuse_first and pipeline:
+            raise ValueError("capture(): pipeline prefetches a first half that reuse_first would not replay; pick one")
+        self.reuse_first = bool(reuse_first)
         self.pipeline = bool(pipeline)
+        self.split = self.pipeline or self.reuse_first      # two graphs (first half / second half) or one
         self.graph_first = None
         self._primed = False
+        self.first_replays = 0
 
         def run():
             op.accumulate_into(self.v, self.out, dot_with=self.v, dot_out=self.dot, ws=self.ws, ops=kernels)
@@ -283,8 +320,8 @@ class GraphedHVP:
             with _math_sdpa():
                 for i in range(len(op.batches)):
                     op._first_backward(i)
-        if self.pipeline:
-            op.cache_graph = True               # run() then only performs the second backward over the graphs first_half() built
+        # the capture decides the caching policy itself (no memory query while a capture is open)
+        op.cache_graph = True if self.split else False   # split: run() performs only the second backward over first_half()'s graphs
         # A cached first-backward graph must be (re)built on the side stream: autograd replays each node on
         # the stream its forward ran on, and a capture may fork into a side stream but never into the legacy
         # default stream (cudaErrorStreamCaptureInvalidated).
@@ -293,14 +330,14 @@ class GraphedHVP:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), _capturable_scalar_tensors():
             for _ in range(max(1, warmup)):
-                if self.pipeline:
+                if self.split:
                     op.clear_cache()
                     first_half()
                 run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         before, h2d0 = kernels.launch_count, op.h2d_bytes
-        if self.pipeline:
+        if self.split:
             # two graphs over ONE memory pool: the second backward reads the activations / first-order gradients the
             # first graph leaves behind; they are always replayed in capture order and never concurrently
             op.clear_cache()
@@ -319,17 +356,20 @@ class GraphedHVP:
             with torch.cuda.graph(self.graph), _capturable_scalar_tensors():
                 run()
         self.launches_per_replay = kernels.launch_count - before
-        self.h2d_bytes_per_replay = op.h2d_bytes - h2d0     # pinned-host batches: copied by the graph on every replay
+        self.h2d_bytes_per_replay = op.h2d_bytes - h2d0     # pinned-host batches: copied by the graph that runs the forward pass
+        op.h2d_bytes = h2d0                                  # capture and warm-up are setup, not applications
         self.applications = 0
 
-    # -- pipelined mode: the v-independent half of the next application runs ahead on a side stream --------------
+    # -- the v-independent half ------------------------------------------------------------------------------------
     def _launch_first(self, main) -> None:
+        """pipelined mode: next application's forward + first backward on the side stream"""
         self._ev_second.record(main)                        # everything this application read is finished with
         self.side.wait_event(self._ev_second)
         with torch.cuda.stream(self.side):
             self.graph_first.replay()
             self._ev_first.record(self.side)
         self.op.h2d_bytes += self.h2d_bytes_per_replay
+        self.first_replays += 1
         self._primed = True
 
     def drain(self) -> None:
@@ -338,10 +378,11 @@ class GraphedHVP:
             torch.cuda.current_stream(self.op.device).wait_event(self._ev_first)
 
     def invalidate(self) -> None:
-        """Drop a prefetched first half (call after the model's weights or the batches changed)."""
+        """The first half must be redone before the next application (call after the model's weights or the
+        batches changed, or to account a run's first-backward build inside a timed region)."""
         if self.pipeline and self._primed:
             torch.cuda.current_stream(self.op.device).wait_event(self._ev_first)
-            self._primed = False
+        self._primed = False
 
     @property
     def weights(self):
@@ -354,20 +395,32 @@ class GraphedHVP:
     def accumulate_into(self, v: torch.Tensor, out: torch.Tensor, dot_with=None, dot_out=None,
                         ws=None, ops=None, phases=None) -> None:
         from . import kernels
+        v = v.reshape(-1)
+        if v.numel() != self.n or v.device != self.op.device:
+            raise ValueError(f"captured operator takes a length-{self.n} vector on {self.op.device}, got {v.numel()} on {v.device}")
         main = torch.cuda.current_stream(self.op.device)
         if self.pipeline:
             if not self._primed:
                 self._launch_first(main)
             main.wait_event(self._ev_first)
+        elif self.reuse_first:
+            if not self._primed:                # first application (or after invalidate()): forward + first backward, once
+                self.graph_first.replay()
+                self.op.h2d_bytes += self.h2d_bytes_per_replay
+                self.first_replays += 1
+                self._primed = True
         else:
             self.op.h2d_bytes += self.h2d_bytes_per_replay
-        self.v.copy_(v.reshape(-1))
+        self.v.copy_(v)
         self.graph.replay()
         kernels.launch_count += self.launches_per_replay
         if out.data_ptr() != self.out.data_ptr():
             out.copy_(self.out)
         if dot_out is not None:
-            dot_out.copy_(self.dot)           # dot_with is v itself in the Lanczos loop (alpha = <Hv, v>)
+            if dot_with is None or dot_with.data_ptr() == v.data_ptr():
+                dot_out.copy_(self.dot)       # the captured <Hv, v> (alpha in the Lanczos loop)
+            else:                             # a dot with some other vector is not what the graph computed
+                kernels.dot(out.reshape(-1)[: self.n], dot_with.reshape(-1), dot_out, ws if ws is not None else self.ws)
         if self.pipeline:
             self._launch_first(main)          # next application's forward + first backward, overlapping the caller's work
         self.applications += 1

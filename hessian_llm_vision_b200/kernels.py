@@ -20,6 +20,18 @@ from ._lib import HLVError  # noqa: F401
 launch_count = 0
 
 
+def require_device(device) -> None:
+    """The recurrence runs on a CUDA device or not at all."""
+    if torch.device(device).type != "cuda":
+        raise RuntimeError(f"lanczos: vectors must live on a CUDA device (got {device}); this engine has no CPU path")
+
+
+def compute_device(requested) -> torch.device:
+    """Where the recurrence runs when a caller names ``requested`` as the place it wants the results."""
+    d = torch.device(requested)
+    return d if d.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

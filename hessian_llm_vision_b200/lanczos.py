@@ -25,6 +25,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
 import numpy as np
 import torch
 
+from . import kernels as _kernels      # the CUDA library front end (raises at first use if libhlv.so is not built)
 from . import ritz as _ritz
 
 _ALIGN = 8          # elements: keeps fp32 and bf16 rows 16-byte aligned
@@ -139,7 +140,6 @@ class LanczosResult:
     basis: Optional[torch.Tensor] = None
     n_local: int = 0
     timings: Dict[str, Dict[str, float]] = field(default_factory=dict)
-    _ops: Any = None
 
     @property
     def T(self) -> torch.Tensor:
@@ -163,7 +163,7 @@ class LanczosResult:
         Ysel = torch.from_numpy(np.ascontiguousarray(self.Y[:, idx])).to(torch.float32).to(dev).contiguous()
         ld = (self.n_local + _ALIGN - 1) // _ALIGN * _ALIGN
         out = torch.empty(len(idx), ld, dtype=torch.float32, device=dev)
-        self._ops.ritz_vectors(self.basis, self.m, Ysel, out, self.n_local)
+        _kernels.ritz_vectors(self.basis, self.m, Ysel, out, self.n_local)
         return out[:, : self.n_local]
 
     def eigeninfo(self, basis: bool = False) -> Dict[str, torch.Tensor]:
@@ -182,7 +182,7 @@ class LanczosEngine:
 
     def __init__(self, hvp: Callable, n: int, n_iter: int, device, reorth: Optional[str] = None,
                  basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
-                 breakdown_tol: Optional[float] = None, comm: Optional[Comm] = None, ops=None,
+                 breakdown_tol: Optional[float] = None, comm: Optional[Comm] = None,
                  profile: bool = False, column_vectors: bool = False, cgs_passes: int = 2, fused_cgs: bool = True,
                  reorth_tol: Optional[float] = None):
         if reorth not in (None, "full"):
@@ -191,9 +191,8 @@ class LanczosEngine:
             raise ValueError("basis_dtype must be torch.float32 or torch.bfloat16")
         if n_iter < 1:
             raise ValueError("n_iter must be >= 1")
-        if ops is None:
-            from . import kernels as ops      # the CUDA library; raises if it is not built
-        self.ops = ops
+        ops = self.ops = _kernels
+        ops.require_device(device)            # no CPU path
         self.hvp = hvp
         self.n, self.m = int(n), int(n_iter)
         self.device = torch.device(device)
@@ -275,6 +274,8 @@ class LanczosEngine:
         if normalize:
             v0 = v0 / torch.linalg.vector_norm(v0)
         self.j = 0
+        if hasattr(self.hvp, "invalidate"):
+            self.hvp.invalidate()               # a captured operator redoes its v-independent half for this run
         self.alphas.zero_(); self.betas.zero_(); self.breakdown_iter.fill_(-1)
         local = torch.zeros(self.shard_n, dtype=torch.float32, device=self.device)
         hi = min(self.lo + self.shard_n, self.n)
@@ -321,12 +322,9 @@ class LanczosEngine:
                 r = r.detach().reshape(-1)
                 if r.numel() != n:
                     raise ValueError(f"hvp returned {r.numel()} elements, expected {n}")
-                if r.device != self.device or r.dtype != torch.float32:
-                    r = r.to(device=self.device, dtype=torch.float32)    # slow path (e.g. a closure that ends in .cpu())
-                if G == 1 and n == self.shard_n and r.is_contiguous() and r.data_ptr() % 16 == 0:
-                    self.w = r                                           # adopt the fresh tensor, no copy
-                else:
-                    tgt.copy_(r)
+                # always a copy into the engine's own w (4n bytes: 0.15 ms at GPT-2 size): an operator may return
+                # its input, a view of it, or a buffer it keeps -- w is updated in place by every kernel that follows
+                tgt.copy_(r)                                             # also converts dtype / device (a closure that ends in .cpu())
                 need_dot = True
         if G > 1:
             ph.start("reduce_scatter")
@@ -431,6 +429,8 @@ class LanczosEngine:
     def load_state_dict(self, sd: Dict[str, Any]) -> None:
         if (sd["n"], sd["m"], sd["world"], sd["rank"]) != (self.n, self.m, self.comm.world, self.comm.rank):
             raise ValueError("checkpoint does not match this engine (n, m, world, rank)")
+        if (sd.get("reorth", self.reorth), sd.get("basis_dtype", str(self.basis_dtype))) != (self.reorth, str(self.basis_dtype)):
+            raise ValueError("checkpoint does not match this engine (reorth, basis_dtype)")
         if self.keep_basis and "basis_rows" not in sd:
             raise ValueError("engine keeps a basis but the checkpoint has none")
         j = int(sd["j"])
@@ -468,13 +468,13 @@ class LanczosEngine:
         return LanczosResult(alphas=torch.from_numpy(a32.astype(np.float64)), betas=torch.from_numpy(b32.astype(np.float64)),
                              eigvals=eigvals, gammas=gammas, Y=Y, m=m_eff, n=self.n, breakdown=bd >= 0,
                              basis=self.basis if self.keep_basis else None, n_local=self.shard_n if self.comm.world > 1 else self.n,
-                             timings=self.phases.summary(), _ops=self.ops)
+                             timings=self.phases.summary())
 
 
 def lanczos(hvp: Callable, n_iter: int, v0: torch.Tensor, reorth: Optional[str] = None, *,
             basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
             breakdown_tol: Optional[float] = None, check_every: int = 16, normalize_v0: bool = False,
-            comm: Optional[Comm] = None, ops=None, profile: bool = False, column_vectors: bool = False,
+            comm: Optional[Comm] = None, profile: bool = False, column_vectors: bool = False,
             on_iteration: Optional[Callable[[int, LanczosEngine], None]] = None, fused_cgs: bool = True,
             reorth_tol: Optional[float] = None) -> LanczosResult:
     """Run ``n_iter`` Lanczos iterations of the symmetric operator ``hvp`` from ``v0``.
@@ -494,10 +494,8 @@ def lanczos(hvp: Callable, n_iter: int, v0: torch.Tensor, reorth: Optional[str] 
     (probe_vector / normalize_v0): torch's CPU float32 norm is 1.4% off at 1.2e8 elements.
     """
     dev = v0.device
-    if dev.type != "cuda" and ops is None:
-        raise RuntimeError("lanczos: v0 must live on a CUDA device; this engine has no CPU path")
     eng = LanczosEngine(hvp, v0.numel(), n_iter, dev, reorth=reorth, basis_dtype=basis_dtype,
-                        keep_basis=keep_basis, breakdown_tol=breakdown_tol, comm=comm, ops=ops,
+                        keep_basis=keep_basis, breakdown_tol=breakdown_tol, comm=comm,
                         profile=profile, column_vectors=column_vectors, fused_cgs=fused_cgs, reorth_tol=reorth_tol)
     eng.start(v0, normalize=normalize_v0)
     for j in range(n_iter):
@@ -531,12 +529,7 @@ def lanczos_tridiag(matmul_closure: Callable, max_iter: int, dtype=torch.float32
     P = int(tuple(matrix_shape)[-1])
     if init_vecs is None and getattr(matmul_closure, "init_vec", None) is not None:
         init_vecs = matmul_closure.init_vec          # CurvVecProduct(loader, model, init_vec=...) -- see hvp.py
-    if torch.device(device).type == "cuda":
-        cuda_dev = torch.device(device)
-    elif engine_kwargs.get("ops") is not None and init_vecs is not None:
-        cuda_dev = init_vecs.device                  # test double: stay where the caller's data is
-    else:
-        cuda_dev = torch.device("cuda", torch.cuda.current_device())
+    cuda_dev = _kernels.compute_device(device)       # device='cpu' (gpt2_hessian_cpu.py:209) only moves the RESULTS
     if init_vecs is None:
         init_vecs = torch.randn(P, 1, dtype=torch.float32, device=cuda_dev)
     res = lanczos(matmul_closure, max_iter, init_vecs.reshape(-1).to(cuda_dev), reorth="full",

@@ -63,13 +63,15 @@ def _exchange(comm: Optional[Comm], items: list) -> list:
 
 
 def slq(hvp: Callable, n: int, n_iter: int, seeds: Sequence[int], device, reorth: Optional[str] = "full",
-        basis_dtype: torch.dtype = torch.float32, replicas: Optional[Comm] = None, ops=None,
+        basis_dtype: torch.dtype = torch.float32, replicas: Optional[Comm] = None,
         on_probe: Optional[Callable[[int, LanczosResult], None]] = None) -> SLQResult:
     """One Lanczos run of ``n_iter`` iterations per probe seed; the engine (and its basis
     allocation) is reused across probes.  ``replicas``: deal probes round-robin over the ranks of
-    a process group (each rank must hold the full operator)."""
+    a process group (each rank must hold the full operator).
+    The LanczosResult handed to ``on_probe`` shares the engine's basis buffer: its ``Q`` / ``ritz_vectors()`` are
+    valid only inside the callback (the next probe overwrites the rows); clone what must outlive it."""
     rank, world = (replicas.rank, replicas.world) if replicas is not None else (0, 1)
-    eng = LanczosEngine(hvp, n, n_iter, device, reorth=reorth, basis_dtype=basis_dtype, ops=ops)
+    eng = LanczosEngine(hvp, n, n_iter, device, reorth=reorth, basis_dtype=basis_dtype)
     mine = []
     for k, seed in enumerate(seeds):
         if k % world != rank:
@@ -88,7 +90,7 @@ def slq(hvp: Callable, n: int, n_iter: int, seeds: Sequence[int], device, reorth
 
 def per_block_spectra(model: torch.nn.Module, batches, n_iter: int, blocks: Optional[Sequence[torch.nn.Module]] = None,
                       seed: int = 0, loss_fn: Callable = lm_loss, reorth: Optional[str] = "full",
-                      replicas: Optional[Comm] = None, ops=None, **op_kwargs):
+                      replicas: Optional[Comm] = None, **op_kwargs):
     """visual-eigen.ipynb cell 12: for every transformer block, Lanczos on the Hessian restricted to
     that block's parameters.  Returns (all_eigvals, all_gammas) lists ordered by block index."""
     if blocks is None:
@@ -101,7 +103,7 @@ def per_block_spectra(model: torch.nn.Module, batches, n_iter: int, blocks: Opti
         params = list(blk.parameters())
         op = HessianVectorProduct(model, batches, loss_fn=loss_fn, params=params, **op_kwargs)
         dev = params[0].device
-        eng = LanczosEngine(op, op.n, n_iter, dev, reorth=reorth, ops=ops)
+        eng = LanczosEngine(op, op.n, n_iter, dev, reorth=reorth)
         eng.start(probe_vector(op.n, seed + i, dev))
         for j in range(n_iter):
             eng.step(j)

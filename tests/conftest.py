@@ -22,8 +22,8 @@ def golden_dir():
 def libhlv():
     """The built C-ABI library; built on demand (nvcc cross-compiles without a GPU)."""
     from hessian_llm_vision_b200 import _lib
-    if not os.path.exists(_lib.LIB_PATH):
-        import __graft_entry__
+    import __graft_entry__
+    if not __graft_entry__.library_is_current():      # source hash, not mtimes: never test a stale binary
         __graft_entry__.build()
     return _lib.load()
 

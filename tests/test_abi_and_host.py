@@ -70,7 +70,7 @@ def test_product_has_no_cpu_path():
     with pytest.raises(TypeError, match="CUDA"):
         kernels.gather([torch.zeros(4)], torch.zeros(4))
     # and nothing under the product package imports the oracle
-    pkg = os.path.join(ROOT, "hessian-llm-vision_b200")
+    pkg = os.path.join(ROOT, "hessian_llm_vision_b200")
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("oracle-", ""), fn
@@ -123,6 +123,13 @@ def test_slq_density_integrates_to_one():
 
 
 # ---------------------------------------------------------------- engine host logic (test double)
+@pytest.fixture
+def cpu_double(monkeypatch):
+    """Swap the engine's kernel front end for the oracle-backed CPU test double -- from the TEST side only:
+    the product API has no backend argument."""
+    fake_ops.install(monkeypatch)
+
+
 def _sym(seed, n):
     torch.manual_seed(seed)
     M = torch.randn(n, n)
@@ -133,11 +140,11 @@ def _sym(seed, n):
 
 @pytest.mark.parametrize("reorth", [None, "full"])
 @pytest.mark.parametrize("n", [96, 101])
-def test_engine_control_flow_single_process(reorth, n):
+def test_engine_control_flow_single_process(reorth, n, cpu_double):
     import hessian_llm_vision_b200 as hlv
     M, v0 = _sym(3, n)
     m = 12
-    res = hlv.lanczos(lambda v: M @ v, m, v0, reorth=reorth, ops=fake_ops, keep_basis=True)
+    res = hlv.lanczos(lambda v: M @ v, m, v0, reorth=reorth, keep_basis=True)
     ref = oracle.lanczos_cgs2(lambda v: M @ v, v0, m, reorth=reorth)
     scale = float(ref["T"].abs().max())
     assert float((res.T - ref["T"]).abs().max()) / scale < 2e-5
@@ -147,23 +154,43 @@ def test_engine_control_flow_single_process(reorth, n):
     assert V.shape == (1, n)
     # pieces protocol: list return goes through gather (+ fused alpha)
     sizes = [n // 3, n - n // 3]
-    res2 = hlv.lanczos(lambda v: list(torch.split(M @ v, sizes)), m, v0, reorth=reorth, ops=fake_ops)
+    res2 = hlv.lanczos(lambda v: list(torch.split(M @ v, sizes)), m, v0, reorth=reorth)
     assert float((res2.T - res.T).abs().max()) / scale < 1e-6
 
 
-def test_engine_breakdown_truncates():
+def test_engine_never_adopts_the_operators_buffer(cpu_double):
+    """An operator may return its input (identity, masks, views) or a buffer it keeps: the engine must copy, because
+    w is updated in place by every kernel that follows (round-1 advisor finding: Q[0] was overwritten)."""
+    import hessian_llm_vision_b200 as hlv
+    M, v0 = _sym(4, 64)
+    res = hlv.lanczos(lambda v: v, 3, v0, reorth="full", keep_basis=True, breakdown_tol=1e-5, check_every=1)
+    assert abs(float(res.Q[0].norm()) - 1.0) < 1e-6 and abs(float(res.alphas[0]) - 1.0) < 1e-6 and res.breakdown
+    keep = torch.zeros(64)
+    seen = []
+
+    def op(v):
+        torch.matmul(M, v, out=keep)
+        seen.append(v.clone())
+        return keep                                  # the SAME persistent buffer every time
+    res = hlv.lanczos(op, 6, v0, reorth="full")
+    assert torch.equal(keep, M @ seen[-1])           # not mutated by the recurrence
+    ref = oracle.lanczos_cgs2(lambda v: M @ v, v0, 6, reorth="full")
+    assert float((res.T - ref["T"]).abs().max()) / float(ref["T"].abs().max()) < 2e-5
+
+
+def test_engine_breakdown_truncates(cpu_double):
     import hessian_llm_vision_b200 as hlv
     torch.manual_seed(1)
     U, _ = torch.linalg.qr(torch.randn(64, 3))
     H = (U * torch.tensor([3.0, 2.0, 1.0])) @ U.t()
     v0 = U @ torch.tensor([0.5, 0.5, 0.70710678])
     v0 /= v0.norm()
-    res = hlv.lanczos(lambda v: H @ v, 10, v0, reorth="full", ops=fake_ops, breakdown_tol=1e-5, check_every=1)
+    res = hlv.lanczos(lambda v: H @ v, 10, v0, reorth="full", breakdown_tol=1e-5, check_every=1)
     assert res.breakdown and res.m == 3
     assert np.allclose(res.eigvals.numpy(), [1, 2, 3], atol=1e-4)
 
 
-def test_lanczos_tridiag_shim_shapes():
+def test_lanczos_tridiag_shim_shapes(cpu_double):
     import hessian_llm_vision_b200 as hlv
     M, v0 = _sym(5, 64)
     calls = []
@@ -172,7 +199,7 @@ def test_lanczos_tridiag_shim_shapes():
         calls.append(tuple(v.shape))
         return M @ v
     Q, T = hlv.lanczos_tridiag(closure, max_iter=6, dtype=torch.float32, device="cpu", matrix_shape=(64, 64),
-                               init_vecs=v0.unsqueeze(1), ops=fake_ops)
+                               init_vecs=v0.unsqueeze(1))
     assert Q.shape == (64, 6) and T.shape == (6, 6)
     assert all(s == (64, 1) for s in calls)                     # closure sees [P,1] like gpytorch's
     assert float((Q.t() @ Q - torch.eye(6)).abs().max()) < 1e-5
@@ -185,6 +212,7 @@ import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["HLV_ROOT"])
 import hessian_llm_vision_b200 as hlv
 from tests import fake_ops
+fake_ops.install()
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["HLV_PORT"],
                         rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
@@ -197,7 +225,7 @@ for r in range(world):
 v = torch.randn(n); v0 = v / v.norm()
 mine = Ms[rank] / world
 tol = os.environ.get("HLV_REORTH_TOL", "")
-res = hlv.lanczos(lambda x: mine @ x, m, v0, reorth=os.environ["HLV_REORTH"] or None, ops=fake_ops,
+res = hlv.lanczos(lambda x: mine @ x, m, v0, reorth=os.environ["HLV_REORTH"] or None,
                   comm=hlv.Comm(), keep_basis=True, reorth_tol=float(tol) if tol else None)
 if rank == 0:
     torch.save({"T": res.T, "n_local": res.n_local, "m": res.m}, os.environ["HLV_OUT"])
@@ -237,18 +265,18 @@ def test_sharded_engine_two_ranks_gloo(tmp_path, reorth, n, tol):
 
 
 # ---------------------------------------------------------------- resume, SLQ, per-block (host logic, test double)
-def test_checkpoint_resume_matches_uninterrupted_run():
+def test_checkpoint_resume_matches_uninterrupted_run(cpu_double):
     import hessian_llm_vision_b200 as hlv
     M, v0 = _sym(8, 120)
     m = 16
     for reorth, dt in ((None, torch.float32), ("full", torch.float32), ("full", torch.bfloat16)):
-        full = hlv.lanczos(lambda v: M @ v, m, v0, reorth=reorth, basis_dtype=dt, ops=fake_ops)
-        a = hlv.LanczosEngine(lambda v: M @ v, 120, m, "cpu", reorth=reorth, basis_dtype=dt, ops=fake_ops)
+        full = hlv.lanczos(lambda v: M @ v, m, v0, reorth=reorth, basis_dtype=dt)
+        a = hlv.LanczosEngine(lambda v: M @ v, 120, m, "cpu", reorth=reorth, basis_dtype=dt)
         a.start(v0)
         for j in range(7):
             a.step(j)
         sd = a.state_dict()
-        b = hlv.LanczosEngine(lambda v: M @ v, 120, m, "cpu", reorth=reorth, basis_dtype=dt, ops=fake_ops)
+        b = hlv.LanczosEngine(lambda v: M @ v, 120, m, "cpu", reorth=reorth, basis_dtype=dt)
         b.load_state_dict(sd)
         assert b.j == 7
         for j in range(7, m):
@@ -256,10 +284,10 @@ def test_checkpoint_resume_matches_uninterrupted_run():
         assert torch.equal(b.result().T, full.T)
 
 
-def test_slq_multi_probe_and_block_drivers(golden_dir):
+def test_slq_multi_probe_and_block_drivers(golden_dir, cpu_double):
     import hessian_llm_vision_b200 as hlv
     M, _ = _sym(2, 200)
-    r = hlv.slq(lambda v: M @ v, 200, 20, seeds=[0, 1, 2, 3], device="cpu", ops=fake_ops)
+    r = hlv.slq(lambda v: M @ v, 200, 20, seeds=[0, 1, 2, 3], device="cpu")
     assert r.seeds == [0, 1, 2, 3] and len(r.eigvals) == 4
     d = r.eigeninfo()
     assert abs(float(d["gammas"].sum()) - 1) < 1e-5 and bool((d["eigvals"][1:] >= d["eigvals"][:-1]).all())
@@ -269,14 +297,14 @@ def test_slq_multi_probe_and_block_drivers(golden_dir):
     est = float((d["eigvals"] * d["gammas"]).sum())
     assert abs(est - float(torch.trace(M)) / 200) < 0.5
     # each probe equals a plain lanczos() run from the same probe vector
-    one = hlv.lanczos(lambda v: M @ v, 20, hlv.probe_vector(200, 2, "cpu"), reorth="full", ops=fake_ops)
+    one = hlv.lanczos(lambda v: M @ v, 20, hlv.probe_vector(200, 2, "cpu"), reorth="full")
     assert torch.equal(one.eigvals, r.eigvals[2])
     # per-block spectra on the tiny golden GPT-2 (visual-eigen.ipynb cell 12), CPU test double
     from tests.test_oracle_golden import _tiny_model_from_golden
     g = np.load(os.path.join(golden_dir, "tiny_gpt2_hvp.npz"))
     model = _tiny_model_from_golden(g)
     ids = torch.from_numpy(g["ids"])
-    ev, gm = hlv.per_block_spectra(model, [ids], 4, seed=5, ops=fake_ops)
+    ev, gm = hlv.per_block_spectra(model, [ids], 4, seed=5)
     assert len(ev) == 2 and all(e.shape == (4,) for e in ev)
     blk = list(model.transformer.h[1].parameters())
     nb = sum(p.numel() for p in blk)
@@ -313,14 +341,14 @@ def test_lm_loss_disables_kv_cache_without_changing_the_loss():
     assert torch.equal(hvp.lm_loss(model, ids), model(input_ids=ids, labels=ids).loss)
 
 
-def test_conditional_second_pass_host_logic():
+def test_conditional_second_pass_host_logic(cpu_double):
     """reorth_tol: the second Gram-Schmidt pass's update is predicated on a device flag (gpytorch's "while any
     q_i . r > tol").  tol=0 always applies it (== unconditional CGS2), a huge tol never does; a sensible tol keeps
     T and orthogonality at working precision.  Host logic only (test double on CPU)."""
     import hessian_llm_vision_b200 as hlv
     M, v0 = _sym(11, 400)
     m = 30
-    run = lambda **kw: hlv.lanczos(lambda v: M @ v, m, v0, reorth="full", ops=fake_ops, **kw)
+    run = lambda **kw: hlv.lanczos(lambda v: M @ v, m, v0, reorth="full", **kw)
     base = run()
     scale = float(base.T.abs().max())
     always = run(reorth_tol=0.0)
@@ -354,11 +382,12 @@ import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["HLV_ROOT"])
 import hessian_llm_vision_b200 as hlv
 from tests import fake_ops
+fake_ops.install()
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["HLV_PORT"],
                         rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 torch.manual_seed(2)
 A = torch.randn(150, 150); M = (A + A.t()) / 2
-r = hlv.slq(lambda v: M @ v, 150, 12, seeds=[3, 4, 5, 6, 7], device="cpu", ops=fake_ops, replicas=hlv.Comm())
+r = hlv.slq(lambda v: M @ v, 150, 12, seeds=[3, 4, 5, 6, 7], device="cpu", replicas=hlv.Comm())
 if dist.get_rank() == 0:
     torch.save({"seeds": r.seeds, "eigvals": r.eigvals, "gammas": r.gammas}, os.environ["HLV_OUT"])
 dist.barrier()
@@ -366,7 +395,7 @@ dist.destroy_process_group()
 """
 
 
-def test_slq_probes_dealt_over_two_ranks_gloo(tmp_path):
+def test_slq_probes_dealt_over_two_ranks_gloo(tmp_path, cpu_double):
     """Config 5's multi-GPU shape: probes are independent units, dealt round-robin over the ranks with NO data-path
     collective ("replicas only"); the (eigvals, gammas) pairs are exchanged once at the end and equal a
     single-process run probe for probe."""
@@ -386,7 +415,7 @@ def test_slq_probes_dealt_over_two_ranks_gloo(tmp_path):
     got = torch.load(out)
     torch.manual_seed(2)
     A = torch.randn(150, 150); M = (A + A.t()) / 2
-    one = hlv.slq(lambda v: M @ v, 150, 12, seeds=[3, 4, 5, 6, 7], device="cpu", ops=fake_ops)
+    one = hlv.slq(lambda v: M @ v, 150, 12, seeds=[3, 4, 5, 6, 7], device="cpu")
     assert got["seeds"] == one.seeds == [3, 4, 5, 6, 7]
     for a, b in zip(got["eigvals"], one.eigvals):
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())     # OMP_NUM_THREADS differs between the two runs
