@@ -12,6 +12,12 @@ basis row, normalise + store.  The m=100 run has basis depth j = 0..99; with --s
 the timed region IS that run; with another K, step i runs at depth floor((i+0.5)*100/K) over a
 pre-built orthonormal basis so the mean depth (hence mean cost) is that of the m=100 run.
 
+The forward pass and the first backward of the double-backward do not depend on the Lanczos vector.
+The headline arms (--hvp reuse, the library default) run them ONCE per Lanczos run -- inside the timed
+region, at its first step -- and every iteration then performs the second backward (bit-identical
+results, tests/test_gpu_zz_full_size.py); --hvp rebuild redoes them every iteration like the reference
+(round 1's headline; reported under "extras" at N=1).
+
 Scaling is STRONG: the global batch (8 sequences x 512 tokens, the batch of the reference's logged
 runs) and therefore the operator and T are the same at every N; ranks shard the sequences
 (reduce-scatter of Hv) and the basis along the parameter dimension (k-float all-reduces).
@@ -76,7 +82,13 @@ def parse_args():
                     help="graph mode: capture the application as two graphs and prefetch the v-independent half of iteration j+1 on a "
                          "side stream while the recurrence and collectives of iteration j run.  auto = on for N>1 (+2%% at N=8), off at "
                          "N=1 (+0.5%% there, and the concurrent GEMMs would blur the per-kernel roofline timings)")
-    ap.add_argument("--cache-graph", action="store_true", help="keep the first-backward graph across iterations (extra, not the headline)")
+    ap.add_argument("--hvp", default="reuse", choices=["reuse", "rebuild"],
+                    help="reuse (library default): forward + first backward once per Lanczos run, inside the timed region, then one second "
+                         "backward per iteration; rebuild: the whole double-backward every iteration, like the reference")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1: how Hv shards, Lanczos vectors and Gram-Schmidt coefficients move between ranks.  peer = libhlv kernels over "
+                         "NVLink peer memory (reduce-scatter + alpha, coefficient exchange in the kernels' epilogues/prologues, v written "
+                         "straight into every peer); nccl = torch.distributed collectives; auto = peer when symmetric memory is available")
     ap.add_argument("--hvp-mode", default="graph", choices=["graph", "eager"],
                     help="graph: the whole double-backward (forward, both backward passes, gather) is captured once into a CUDA "
                          "graph and replayed every iteration -- all of the work, none of the ~4,000 Python-issued launches; "
@@ -176,17 +188,32 @@ def ncu_traffic(kernel: str, algorithmic_bytes_per_launch: float):
 
 
 # --------------------------------------------------------------------------- reference's CPU path (oracle port)
+def host_threads() -> int:
+    """All the host threads the box offers.  torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the
+    reference arm runs on rank 0 alone, so it takes the whole machine back explicitly."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def reference_iteration_sampler(model_dev, batches_dev, weights, n, dev, host_rows: int):
     """The faithful gpt2_hessian_cpu.py shape: HVP on the GPU by the reference's own
     formulation (sum(v*g).backward(), torch.cat), `.cpu()` of the result every iteration
-    (gpt2_hessian_cpu.py:137), recurrence + full reorthogonalisation on HOST cores with torch CPU ops.
-    Returns step(depth) -> (t_non_cgs_s, t_cgs_s, rows_used)."""
+    (gpt2_hessian_cpu.py:137), recurrence + full reorthogonalisation on HOST cores with torch CPU ops,
+    against a REAL host-resident basis of ``host_rows`` rows (49.6 GB at depth 100) -- nothing is extrapolated.
+    Returns step(depth) -> seconds (wall, everything included)."""
     import oracle   # CPU baseline leg only (the checker, timed as the baseline -- never the product path)
-    torch.manual_seed(99)
-    Qh = torch.zeros(host_rows, n)
-    for r in range(host_rows):           # synthetic orthonormal-ish host basis (values do not affect timing)
-        Qh[r].normal_()
-        Qh[r] /= Qh[r].norm()
+    g = torch.Generator().manual_seed(99)
+    Qh = torch.empty(host_rows, n)
+    base = torch.randn(n, generator=g)
+    base /= base.double().norm().float()
+    for r in range(host_rows):           # synthetic unit-norm host rows (values do not affect timing; one threaded pass per row)
+        torch.mul(base, 1.0 if r % 2 == 0 else -1.0, out=Qh[r])
+        Qh[r, r::host_rows] *= 0.5       # rows differ, cheaply
     state = {"v": Qh[0].clone(), "v_old": Qh[min(1, host_rows - 1)].clone()}
 
     def step(depth_rows: int):
@@ -196,22 +223,22 @@ def reference_iteration_sampler(model_dev, batches_dev, weights, n, dev, host_ro
         w = w.cpu()                                                                       # D2H, :137
         alpha = torch.dot(w, v)                                                           # lanczostrain_hand.py:200
         w -= (alpha * v + 0.5 * state["v_old"])                                           # :202
-        t1 = time.perf_counter()
         rows = min(depth_rows, host_rows)
         for _ in range(2):                                                                # CGS2 on host cores
             c = Qh[:rows] @ w
             w -= Qh[:rows].t() @ c
-        t2 = time.perf_counter()
         b = torch.norm(w, 2)                                                              # :190-193
         state["v_old"], state["v"] = v, w / b
-        t3 = time.perf_counter()
-        return (t1 - t0) + (t3 - t2), (t2 - t1), rows
+        if rows < host_rows:
+            Qh[rows].copy_(state["v"])                                                    # :194  Q[i+1] = v
+        return time.perf_counter() - t0
     return step
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    cores = host_threads()
     dev = torch.device("cuda:0")
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
@@ -221,29 +248,27 @@ def run_reference(args, rank, world):
     batches = [b.to(dev) for b in make_tokens(cfg, args.global_batch, args.micro_batch, seq)]
     weights = [b.shape[0] / args.global_batch for b in batches]
     n = sum(p.numel() for p in model.parameters())
-    host_rows = 8
-    step = reference_iteration_sampler(model, batches, weights, n, dev, host_rows)
     sched = depth_schedule(args.steps)
+    host_rows = max(sched) + 1
+    step = reference_iteration_sampler(model, batches, weights, n, dev, host_rows)
     for i in range(args.warmup):
         step(sched[i % len(sched)] + 1)
     clocks = ClockSampler(0); clocks.start()
     t_wall0 = time.perf_counter()
-    est = 0.0
     for j in sched:
-        t_fix, t_cgs, rows = step(j + 1)
-        est += t_fix + t_cgs * (j + 1) / rows          # CGS cost is linear in the number of rows
+        step(j + 1)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t_wall0
-    value = args.steps / est
-    cores = torch.get_num_threads()
-    sample = (f"{args.steps} iterations: real GPU HVP ({args.global_batch}x{seq} tokens) + .cpu() + host three-term update each; "
-              f"host CGS2 timed on {host_rows} resident rows and scaled linearly to the scheduled depth "
-              f"(mean depth {sum(sched) / len(sched) + 1:.1f} rows); wall {wall:.1f}s, scaled {est:.1f}s")
+    value = args.steps / wall
+    sample = (f"{args.steps} iterations, every one measured in full: GPU HVP by the reference's formulation ({args.global_batch}x{seq} tokens) "
+              f"+ .cpu() + host three-term update + host CGS2 against a real {host_rows}-row host basis ({host_rows * n * 4 / 1e9:.1f} GB) at the "
+              f"scheduled depth (mean {sum(sched) / len(sched) + 1:.1f} rows) with {cores} host threads; wall {wall:.1f}s")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * est / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": bench_config(args, seq, n),
-            "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample,
+                             "os_cpu_count": os.cpu_count()},
             "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "clocks": clocks.stop(), "gpu_launches": 0}
     emit(line)
@@ -279,20 +304,22 @@ def run_ours(args, rank, world, local_rank):
     all_batches = make_tokens(cfg, args.global_batch, args.micro_batch, seq)
     mine_host = [b.pin_memory() for b in hlv.shard_batches(all_batches, rank, world)]
     mine_dev = [b.to(dev) for b in mine_host]
-    op_dev = hlv.HessianVectorProduct(model, mine_dev, total_sequences=args.global_batch, cache_graph=args.cache_graph)
-    op_host = hlv.HessianVectorProduct(model, mine_host, total_sequences=args.global_batch, device=dev)
+    reuse = args.hvp == "reuse"
+    new_op = lambda batches, keep: hlv.HessianVectorProduct(model, batches, total_sequences=args.global_batch, cache_graph=keep, device=dev)
+    op_dev, op_host = new_op(mine_dev, reuse), new_op(mine_host, reuse)
     hvp_modes = {}
 
-    def graphed(op, tag):
-        """The operator the timed loop uses: the same double-backward, replayed from a CUDA graph (or eager)."""
+    def graphed(op, tag, keep_first):
+        """The operator the timed loop uses: the same double-backward, replayed from CUDA graphs (or eager)."""
         if args.hvp_mode != "graph":
-            hvp_modes[tag] = "eager"
+            hvp_modes[tag] = "eager, " + ("first-backward graph kept for the run" if keep_first else "rebuilt every iteration")
             return op
         try:
-            pipe = args.pipeline == "on" or (args.pipeline == "auto" and world > 1)
-            g = op.capture(out=eng.w if world == 1 else eng.hv_full, pipeline=pipe)
-            hvp_modes[tag] = ("cuda_graph (forward + both backward passes + gather replayed every iteration"
-                              + ("; the v-independent half of iteration j+1 overlaps the recurrence of iteration j on a side stream)" if pipe else ")"))
+            pipe = (not keep_first) and (args.pipeline == "on" or (args.pipeline == "auto" and world > 1))
+            g = op.capture(out=eng.w if world == 1 else eng.hv_full, pipeline=pipe, reuse_first=keep_first)
+            hvp_modes[tag] = ("cuda_graph: " + ("forward + first backward replayed ONCE per run inside the timed region, second backward + gather every iteration"
+                                                if keep_first else "forward + both backward passes + gather replayed every iteration")
+                              + ("; the v-independent half of iteration j+1 overlaps the recurrence of iteration j on a side stream" if pipe else ""))
             return g
         except Exception as e:  # noqa: BLE001  -- a model that cannot be captured still benches, eagerly
             hvp_modes[tag] = f"eager (capture failed: {repr(e)[:200]})"
@@ -300,7 +327,7 @@ def run_ours(args, rank, world, local_rank):
             return op
     basis_dtype = torch.float32 if args.basis_dtype == "f32" else torch.bfloat16
     eng = hlv.LanczosEngine(op_dev, n, M_DEPTH, dev, reorth="full", basis_dtype=basis_dtype, comm=comm, profile=True,
-                            fused_cgs=not args.no_fused, reorth_tol=args.reorth_tol)
+                            fused_cgs=not args.no_fused, reorth_tol=args.reorth_tol, exchange=args.exchange)
     torch.manual_seed(7)                                  # probe: randn(P)/norm, diego_pythia.py:147-149
     v0 = torch.randn(n)
     v0 = v0.to(dev)                                       # normalise ON THE DEVICE: torch's CPU float32 norm of 1.24e8 elements
@@ -322,7 +349,11 @@ def run_ours(args, rank, world, local_rank):
     def timed(op, e2e: bool):
         eng.hvp = op
         if real_run:
-            eng.start(v0)
+            eng.start(v0)                                 # also invalidates a captured operator's first half
+        elif hasattr(op, "invalidate"):
+            op.invalidate()                               # the run's forward + first backward belong to the timed region
+        elif hasattr(op, "clear_cache"):
+            op.clear_cache()
         eng.phases.pairs.clear()
         comm.barrier(); torch.cuda.synchronize()
         clocks = ClockSampler(local_rank)
@@ -353,14 +384,17 @@ def run_ours(args, rank, world, local_rank):
             eng.v_full.normal_(generator=g).mul_(1.0 / n ** 0.5)
     else:
         prefill()
-    run_dev = graphed(op_dev, "value")
+    run_dev = graphed(op_dev, "value", reuse)
     eng.hvp = run_dev
     for i in range(max(args.warmup, 0)):
         eng.step(sched[i % len(sched)])
     torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats(dev)
 
     ms, launches, clocks, phases = timed(run_dev, e2e=False)
     value = args.steps / (ms / 1e3)
+    peak_bytes = torch.cuda.max_memory_allocated(dev)
+    first_half_runs = getattr(run_dev, "first_replays", None)
     ritz_top = None
     if real_run:
         res = eng.result()
@@ -369,40 +403,54 @@ def run_ours(args, rank, world, local_rank):
     e2e = None
     del run_dev
     eng.hvp = op_dev
+    op_dev.clear_cache()
     torch.cuda.empty_cache()
     if not args.no_e2e:
-        run_host = graphed(op_host, "e2e")
+        run_host = graphed(op_host, "e2e", reuse)
         eng.hvp = run_host
         for i in range(min(max(args.warmup, 0), 1)):
             eng.step(sched[i % len(sched)])
         h2d0 = op_host.h2d_bytes
         ms_e, _, _, _ = timed(run_host, e2e=True)
+        h2d = op_host.h2d_bytes - h2d0
         del run_host
         eng.hvp = op_dev
+        op_host.clear_cache()
         torch.cuda.empty_cache()
         e2e = {"value": args.steps / (ms_e / 1e3), "unit": "iterations/s",
-               "h2d_bytes_per_step": (op_host.h2d_bytes - h2d0) // args.steps, "d2h_bytes_per_step": 16,
-               "ms_per_step": ms_e / args.steps,
-               "api": "LanczosEngine.step over HessianVectorProduct with pinned-host token batches (copied H2D inside every "
-                      "application); alpha/beta read back every step", "hvp_mode": hvp_modes.get("e2e")}
+               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": 16,
+               "h2d_bytes_total": h2d, "ms_per_step": ms_e / args.steps,
+               "api": "LanczosEngine.step over HessianVectorProduct with pinned-host token batches; alpha/beta read back every step.  "
+                      + ("The tokens feed only the forward pass, which --hvp reuse runs once per Lanczos run (inside the timed region): they are "
+                         "copied H2D when it runs, h2d_bytes_per_step = that total / steps" if reuse else
+                         "The tokens are copied H2D inside every application"),
+               "hvp_mode": hvp_modes.get("e2e")}
 
-    # ---- extras (NOT the headline): the product's faster HVP modes, same metric, same steps --------------
-    # The headline arms above rebuild the whole double-backward every iteration, exactly like the reference.
-    # The first-backward graph does not depend on v, so the operator can keep it (cache_graph=True) and an
-    # iteration then costs one second-backward pass; that pass can additionally be replayed from a CUDA graph.
+    # ---- extras (NOT the headline) ---------------------------------------------------------------------------
+    # The other HVP policy, same metric, same steps: with --hvp reuse (default) this is round 1's headline arm, which
+    # redoes forward + first backward every iteration like the reference; plus the eager (no CUDA graph) variant.
     extras = {}
     if (args.extras or world == 1) and not args.no_extras:
         try:
-            op_c = hlv.HessianVectorProduct(model, mine_dev, total_sequences=args.global_batch, cache_graph=True)
-            op_c.clear_cache()
-            ms_c, _, _, _ = timed(op_c, e2e=False)          # the graph is built inside the timed region (step 0)
-            extras["hvp_cached_first_backward"] = {"value": args.steps / (ms_c / 1e3), "ms_per_step": ms_c / args.steps,
-                                                   "note": "first-backward graph built once inside the timed region, then one second-backward pass per iteration"}
-            gop = op_c.capture()
-            ms_g, _, _, _ = timed(gop, e2e=False)
-            extras["hvp_cached_plus_cuda_graph"] = {"value": args.steps / (ms_g / 1e3), "ms_per_step": ms_g / args.steps,
-                                                    "note": "as above, second backward + gather replayed from a CUDA graph captured before the run (setup, not timed)"}
-            del gop, op_c
+            other = not reuse
+            op_x = new_op(mine_dev, other)
+            gop = graphed(op_x, "extra", other)
+            eng.hvp = gop
+            eng.step(sched[0])
+            ms_x, _, _, _ = timed(gop, e2e=False)
+            extras["hvp_reuse_first_backward" if other else "hvp_rebuilt_every_iteration"] = {
+                "value": args.steps / (ms_x / 1e3), "ms_per_step": ms_x / args.steps, "hvp_mode": hvp_modes.get("extra")}
+            del gop
+            op_x.clear_cache()
+            torch.cuda.empty_cache()
+            op_e = new_op(mine_dev, reuse)
+            ms_g, _, _, _ = timed(op_e, e2e=False)
+            extras["hvp_eager_no_cuda_graph"] = {"value": args.steps / (ms_g / 1e3), "ms_per_step": ms_g / args.steps,
+                                                 "note": "the headline policy issued from Python (no CUDA graph)"}
+            op_e.clear_cache()
+            del op_e, op_x
+            eng.hvp = op_dev
+            torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
             extras["error"] = repr(e)[:300]
 
@@ -412,14 +460,17 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     s = 4 if args.basis_dtype == "f32" else 2
     n_loc = eng.shard_n if world > 1 else n
+    G = world
     kern_bytes = {
         "cgs_project": lambda d: (d["rows"] * s + 4 * d["calls"]) * n_loc,
+        "update_project": lambda d: (d["rows"] * s + 8 * d["calls"]) * n_loc,     # three-term update folded into the first projection: w read + written
         "cgs_update": lambda d: (d["rows"] * s + 8 * d["calls"]) * n_loc,
         "cgs_update_project": lambda d: (d["rows"] * s + 8 * d["calls"]) * n_loc,   # V once; w read + written
         "update": lambda d: 16 * n_loc * d["calls"],
-        "normalize": lambda d: (4 + s) * n_loc * d["calls"] if s == 4 else (4 + 4 + s) * n_loc * d["calls"],
+        "normalize": lambda d: ((4 + s) if s == 4 else (4 + 4 + s)) * n_loc * d["calls"] + (4 * n_loc * (G - 1) * d["calls"] if eng.peer else 0),
         "gather": lambda d: (8 + 4) * n * d["calls"],      # read pieces 4n + write w 4n (+4n v for the fused alpha on the last micro-batch)
         "dot": lambda d: 8 * n_loc * d["calls"],
+        "reduce_scatter_alpha": lambda d: (4 * G + 4 + 4) * n_loc * d["calls"],   # G shards in (G-1 over NVLink), w out, v in
     }
     kernels_out = {}
     for name, fn in kern_bytes.items():
@@ -439,14 +490,16 @@ def run_ours(args, rank, world, local_rank):
                     "value_frac_of_roofline": (value * bound_ms / 1e3) if bound_ms else None,
                     "note": "recurrence kernels only (the libhlv launches timed by CUDA events; a gather captured inside the HVP graph is "
                             "not listed); the step as a whole is bound by the torch HVP, see hvp_ms_per_step"}
-    top = max((k for k in kernels_out if k.startswith("cgs")), key=lambda k: kernels_out[k]["ms_total"], default=None)
+    top = max((k for k in kernels_out if k.startswith("cgs") or k == "update_project"), key=lambda k: kernels_out[k]["ms_total"], default=None)
     roofline = None
     if top:
-        kname = f"hlv::{top}_kernel<{'float' if s == 4 else 'bf16'}>"
+        cname = {"update_project": "cgs_project"}.get(top, top)
+        kname = f"hlv::{cname}_kernel<{'float' if s == 4 else 'bf16'}>"
         roofline = {"bound": "hbm", "kernel": kname, "achieved": kernels_out[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels_out[top]["frac_of_peak"], "bytes_per_launch": kernels_out[top]["bytes_per_launch"],
                     "traffic": ncu_traffic(top, kernels_out[top]["bytes_per_launch"]), "peak_source": peak_src,
-                    "bytes_model": "project: (rows*s+4)*n; update and fused update_project: (rows*s+8)*n per launch (DESIGN.md section 3)",
+                    "bytes_model": "project: (rows*s+4)*n (+4n when it also applies the three-term update); update and fused update_project: "
+                                   "(rows*s+8)*n per launch (DESIGN.md section 3)",
                     "share_of_step": round(kernels_out[top]["ms_total"] / ms, 4)}
     line = {"metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -457,23 +510,28 @@ def run_ours(args, rank, world, local_rank):
                                 "note": "sum of libhlv kernel time (CUDA events) in the timed region; HVP (torch) excluded"},
             "hvp_ms_per_step": phases.get("hvp", {}).get("ms", 0.0) / args.steps,
             "phases_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in phases.items()},
+            "hvp_policy": {"mode": args.hvp, "first_half_runs_in_timed_region": first_half_runs,
+                           "peak_device_bytes": peak_bytes, "kept_first_backward_graph_bytes": getattr(op_dev, "cached_bytes", None)},
+            "exchange": eng.exchange_mode,
             "hvp_mode": hvp_modes.get("value"), "ritz_top3": ritz_top, "extras": extras}
-    # ---- CPU baseline: the reference's CPU path on this box's host cores (rank 0, N=1 only) ----
+    # ---- CPU baseline: the reference's CPU path on this box's host cores (rank 0, N=1 only), a bounded sample ----
     if world == 1 and not args.no_cpu_baseline:
         del eng
         torch.cuda.empty_cache()
-        host_rows = 8
+        cores = host_threads()
+        k_s = 6                                           # 6 iterations spread over the m=100 depth range (~10-15 s of host work)
+        sched_s = depth_schedule(k_s)
+        host_rows = max(sched_s) + 1
         step = reference_iteration_sampler(model, mine_dev, op_dev.weights, n, dev, host_rows)
-        step(host_rows)                                   # warm
-        reps, t_fix, t_cgs = 3, 0.0, 0.0
-        for _ in range(reps):
-            a, b, rows = step(host_rows)
-            t_fix += a / reps; t_cgs += b / reps
-        mean_rows = sum(depth_schedule(M_DEPTH)) / M_DEPTH + 1
-        t_iter = t_fix + t_cgs * mean_rows / host_rows
-        line["cpu_baseline"] = {"value": 1.0 / t_iter, "unit": "iterations/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{reps} iterations of the gpt2_hessian_cpu.py shape (GPU HVP + .cpu() + host recurrence {t_fix:.2f}s; "
-                                          f"host CGS2 on {host_rows} rows {t_cgs:.2f}s scaled linearly to the m=100 mean depth {mean_rows:.1f} rows)",
+        step(sched_s[0] + 1)                              # warm
+        t0 = time.perf_counter()
+        for j in sched_s:
+            step(j + 1)
+        t_s = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": k_s / t_s, "unit": "iterations/s", "cores": cores, "kind": "port",
+                                "sample": f"{k_s} iterations of the gpt2_hessian_cpu.py shape measured in full (GPU HVP + .cpu() + host recurrence + host CGS2 "
+                                          f"against a real {host_rows}-row host basis) at depths {[j + 1 for j in sched_s]} (mean {sum(sched_s) / k_s + 1:.1f} rows, "
+                                          f"the m=100 run's mean is 50.5); {t_s:.1f}s",
                                 "os_cpu_count": os.cpu_count()}
     emit(line)
 
@@ -481,8 +539,8 @@ def run_ours(args, rank, world, local_rank):
 def main():
     args = parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.micro_batch <= 0:
-        args.micro_batch = max(1, min(8, args.global_batch // max(world if args.impl == "ours" else 1, 1)))
+    if args.micro_batch <= 0:               # same rule in both arms, from --gpus, so that the two lines carry the same config
+        args.micro_batch = max(1, min(8, args.global_batch // max(args.gpus, 1)))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

@@ -140,6 +140,7 @@ class LanczosResult:
     basis: Optional[torch.Tensor] = None
     n_local: int = 0
     timings: Dict[str, Dict[str, float]] = field(default_factory=dict)
+    conditional_passes: Optional[int] = None      # reorth_tol runs: iterations whose last Gram-Schmidt pass was applied
 
     @property
     def T(self) -> torch.Tensor:
@@ -184,7 +185,7 @@ class LanczosEngine:
                  basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
                  breakdown_tol: Optional[float] = None, comm: Optional[Comm] = None,
                  profile: bool = False, column_vectors: bool = False, cgs_passes: int = 2, fused_cgs: bool = True,
-                 reorth_tol: Optional[float] = None):
+                 reorth_tol: Optional[float] = None, exchange: str = "auto"):
         if reorth not in (None, "full"):
             raise ValueError("reorth must be None or 'full'")
         if basis_dtype not in (torch.float32, torch.bfloat16):
@@ -251,7 +252,11 @@ class LanczosEngine:
             if not (self.fused and self.cgs_passes == 2):
                 raise ValueError("reorth_tol needs the fused two-pass Gram-Schmidt path (reorth='full', cgs_passes=2, fused_cgs on)")
             self.pass_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.pass_count = torch.zeros(1, dtype=torch.int32, device=self.device)    # iterations whose last pass was applied
             self.norm2_b = torch.zeros(1, **f64)
+        # how shards / coefficients move between ranks: "nccl" = torch.distributed collectives
+        self.peer = None
+        self.exchange_mode = "none" if G == 1 else "nccl"
         self.j = 0
         self.launches = 0
 
@@ -277,6 +282,8 @@ class LanczosEngine:
         if hasattr(self.hvp, "invalidate"):
             self.hvp.invalidate()               # a captured operator redoes its v-independent half for this run
         self.alphas.zero_(); self.betas.zero_(); self.breakdown_iter.fill_(-1)
+        if self.reorth_tol is not None:
+            self.pass_count.zero_()
         local = torch.zeros(self.shard_n, dtype=torch.float32, device=self.device)
         hi = min(self.lo + self.shard_n, self.n)
         if hi > self.lo:
@@ -378,6 +385,7 @@ class LanczosEngine:
                 # cur = V w' and norm2 = |w'|^2 were measured by the fused pass: is w' orthogonal enough already?
                 comm.all_reduce_sum(self.norm2)
                 ops.cgs_needs_pass(cur, rows, self.norm2, self.reorth_tol, self.pass_flag)
+                self.pass_count.add_(self.pass_flag)
                 self.norm2_b.zero_()
                 ph.start("cgs_update")
                 ops.cgs_update(self.basis, rows, cur, self.w, self.norm2_b, self.ws, run_flag=self.pass_flag)
@@ -468,7 +476,8 @@ class LanczosEngine:
         return LanczosResult(alphas=torch.from_numpy(a32.astype(np.float64)), betas=torch.from_numpy(b32.astype(np.float64)),
                              eigvals=eigvals, gammas=gammas, Y=Y, m=m_eff, n=self.n, breakdown=bd >= 0,
                              basis=self.basis if self.keep_basis else None, n_local=self.shard_n if self.comm.world > 1 else self.n,
-                             timings=self.phases.summary())
+                             timings=self.phases.summary(),
+                             conditional_passes=int(self.pass_count.item()) if self.reorth_tol is not None else None)
 
 
 def lanczos(hvp: Callable, n_iter: int, v0: torch.Tensor, reorth: Optional[str] = None, *,
@@ -519,7 +528,11 @@ def lanczos_tridiag(matmul_closure: Callable, max_iter: int, dtype=torch.float32
     CUDA device (``device='cpu'`` only moves the RESULTS to the host, as gpt2_hessian_cpu.py
     expects); a single probe vector (num_init_vecs=1, no batch_shape) is supported; ``init_vecs``
     defaults to randn(P,1) and is normalised, exactly like gpytorch -- the reference's
-    ``init_vec`` swap inside CurvVecProduct (quirk F3) is therefore not needed: pass init_vecs."""
+    ``init_vec`` swap inside CurvVecProduct (quirk F3) is therefore not needed: pass init_vecs.
+    ``tol`` is accepted for signature compatibility: by default BOTH Gram-Schmidt passes always run, which is
+    at least as strong as gpytorch's "re-orthogonalise while any q_i . r > tol"; pass ``reorth_tol=tol`` to get
+    the conditional rule itself (checked in tests/ against a restatement of SURVEY Appendix B -- parity
+    unpinned at that boundary).  Like gpytorch, at most ``matrix_shape[-1]`` iterations run."""
     if dtype != torch.float32:
         raise NotImplementedError("lanczos_tridiag: only float32 (the reference's dtype) is supported")
     if num_init_vecs != 1 or (batch_shape is not None and len(tuple(batch_shape)) > 0):
@@ -532,7 +545,7 @@ def lanczos_tridiag(matmul_closure: Callable, max_iter: int, dtype=torch.float32
     cuda_dev = _kernels.compute_device(device)       # device='cpu' (gpt2_hessian_cpu.py:209) only moves the RESULTS
     if init_vecs is None:
         init_vecs = torch.randn(P, 1, dtype=torch.float32, device=cuda_dev)
-    res = lanczos(matmul_closure, max_iter, init_vecs.reshape(-1).to(cuda_dev), reorth="full",
+    res = lanczos(matmul_closure, min(int(max_iter), P), init_vecs.reshape(-1).to(cuda_dev), reorth="full",
                   normalize_v0=True, column_vectors=True, breakdown_tol=1e-6, **engine_kwargs)
     Q = res.Q.t()                       # [P, m] view of the row-major device basis
     T = res.T

@@ -206,6 +206,56 @@ def test_lanczos_tridiag_shim_shapes(cpu_double):
     assert float((Q.t() @ M @ Q - T).abs().max()) < 1e-3
 
 
+def _cancelling_operator(n, eps, seed, device="cpu"):
+    """eps * (symmetric) + v0 z^T: every A q_k carries an O(1) component along q_0 that the three-term recurrence does
+    not remove, so the Gram-Schmidt pass cancels ~1/eps of the vector's norm and leaves projections ~1e-7/eps -- the
+    situation gpytorch's "while any q_i . r > 1e-5" loop exists for (a noisy or inexact HVP is the practical analogue)."""
+    g = torch.Generator().manual_seed(seed)
+    S = torch.randn(n, n, generator=g)
+    S = (S + S.t()) / 2 / n ** 0.5
+    v0 = torch.randn(n, generator=g)
+    v0 /= v0.norm()
+    z = torch.randn(n, generator=g)
+    return S, v0, z
+
+
+def test_lanczos_tridiag_shim_vs_gpytorch_like_oracle_host_logic(cpu_double):
+    """Host logic of the gpytorch-boundary shim against oracle.gpytorch_like_tridiag (parity
+    unpinned): same T, same Lanczos vectors; the conditional pass fires on both sides in the cancelling case and on
+    neither for a plain symmetric operator; breakdown size."""
+    import hessian_llm_vision_b200 as hlv
+    M, v0 = _sym(21, 160)
+    m = 14
+    ref = oracle.gpytorch_like_tridiag(lambda x: M @ x, v0 * 3, m)
+    Q, T = hlv.lanczos_tridiag(lambda q: M @ q, max_iter=m, dtype=torch.float32, device="cpu", matrix_shape=(160, 160),
+                               init_vecs=(v0 * 3).unsqueeze(1), reorth_tol=1e-5)
+    scale = float(ref["T"].abs().max())
+    assert float((T - ref["T"]).abs().max()) / scale < 1e-5
+    assert float((Q - ref["Q"]).abs().max()) < 5e-4
+    res = hlv.lanczos(lambda q: M @ q, m, v0, reorth="full", reorth_tol=1e-5)
+    assert res.conditional_passes == 0 and sum(ref["extra_passes"]) == 0
+    # cancelling operator: gpytorch's own tol = 1e-5 fires
+    S, v0, z = _cancelling_operator(400, 1e-3, seed=1)
+    op = lambda x: 1e-3 * (S @ x.reshape(-1)) + v0 * torch.dot(z, x.reshape(-1))
+    op64 = lambda x: 1e-3 * (S.double() @ x) + v0.double() * torch.dot(z.double(), x)
+    ref = oracle.gpytorch_like_tridiag(op, v0, m)
+    ref64 = oracle.gpytorch_like_tridiag(op64, v0.double(), m, dtype=torch.float64)
+    scale = float(ref["T"].abs().max())
+    floor = float((ref["T"].double() - ref64["T"]).abs().max()) / scale          # the fp32 oracle's own distance from fp64
+    res = hlv.lanczos(op, m, v0, reorth="full", reorth_tol=1e-5)
+    assert sum(ref["extra_passes"]) > 0 and res.conditional_passes > 0
+    assert float((res.T - ref["T"]).abs().max()) / scale < 1e-5 + floor
+    assert float((res.T.double() - ref64["T"]).abs().max()) / scale < 1e-5 + floor
+    G = res.Q.double() @ res.Q.double().t()
+    assert float((G - torch.eye(m, dtype=torch.float64)).abs().max()) < 5e-6
+    d = (torch.tensor([1.0, 2.0, 3.0, 5.0]) * 1e-3).repeat_interleave(40)
+    _, v0 = _sym(21, 160)
+    ref = oracle.gpytorch_like_tridiag(lambda x: d * x, v0, 9)
+    Q, T = hlv.lanczos_tridiag(lambda q: d.unsqueeze(1) * q, max_iter=9, dtype=torch.float32, device="cpu",
+                               matrix_shape=(160, 160), init_vecs=v0.unsqueeze(1), check_every=1)
+    assert ref["m_eff"] == 4 and T.shape == (4, 4) and Q.shape == (160, 4)
+
+
 # ---------------------------------------------------------------- 2-rank gloo: sharded basis + batch-sharded HVP
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist

@@ -226,6 +226,73 @@ def test_lanczos_tridiag_shim_on_gpu(hlv, cuda_dev):
     assert not Qc.is_cuda and not Tc.is_cuda
 
 
+def _planted(n, eigs, seed):
+    g = torch.Generator().manual_seed(seed)
+    U, _ = torch.linalg.qr(torch.randn(n, n, generator=g, dtype=torch.float64))
+    A = ((U * eigs.double()) @ U.t()).float()
+    return A, torch.randn(n, generator=g)
+
+
+def test_lanczos_tridiag_shim_vs_gpytorch_like_oracle(hlv, cuda_dev):
+    """The gpytorch boundary (gpt2_hessian_cpu.py:207-213), PARITY UNPINNED: gpytorch is not available, so the shim
+    is compared with oracle.gpytorch_like_tridiag -- SURVEY Appendix B restated from documentation.  Covers: the
+    conditional rule with gpytorch's tol on a clustered symmetric spectrum (never fires, on either side), on an
+    operator whose Gram-Schmidt pass cancels ~1000x of the vector (fires on both sides), an un-normalised init
+    vector, the unconditional default, breakdown, max_iter > P."""
+    from tests.test_abi_and_host import _cancelling_operator
+    n, m = 600, 24
+    centers = torch.tensor([1.0, 2.0, 3.0, 5.0, 8.0, 13.0])
+    g = torch.Generator().manual_seed(9)
+    A, v = _planted(n, (centers[:, None] + 1e-3 * torch.randn(6, 100, generator=g)).reshape(-1), seed=2)
+    Ad = A.to(cuda_dev)
+    closure = lambda q: Ad @ q
+    ref = oracle.gpytorch_like_tridiag(lambda x: A @ x, v * 2.5, m)
+    scale = float(ref["T"].abs().max())
+    Q, T = hlv.lanczos_tridiag(closure, max_iter=m, dtype=torch.float32, device="cuda", matrix_shape=(n, n),
+                               init_vecs=(v * 2.5).to(cuda_dev).unsqueeze(1), tol=1e-5, reorth_tol=1e-5)
+    assert Q.shape == (n, m) and T.shape == (m, m)
+    assert _rel(T, ref["T"], scale) < 1e-5                                   # alpha/beta per iteration
+    Qd = Q.double()
+    assert float((Qd.t() @ Qd - torch.eye(m, dtype=torch.float64, device=cuda_dev)).abs().max()) < 5e-6
+    assert float((Q.cpu() - ref["Q"]).abs().max()) < 5e-4                    # same Lanczos vectors, same signs
+    res = hlv.lanczos(closure, m, (v / v.norm()).to(cuda_dev), reorth="full", reorth_tol=1e-5)
+    assert res.conditional_passes == 0 and sum(ref["extra_passes"]) == 0
+    # cancelling operator: the conditional pass fires with gpytorch's own tol, on both sides
+    mc = 14
+    S, v0, z = _cancelling_operator(400, 1e-3, seed=1)
+    Sd, v0d, zd = S.to(cuda_dev), v0.to(cuda_dev), z.to(cuda_dev)
+    op = lambda x: 1e-3 * (S @ x) + v0 * torch.dot(z, x)
+    op64 = lambda x: 1e-3 * (S.double() @ x) + v0.double() * torch.dot(z.double(), x)
+    op_gpu = lambda x: 1e-3 * (Sd @ x) + v0d * torch.dot(zd, x)
+    refc = oracle.gpytorch_like_tridiag(op, v0, mc)
+    refc64 = oracle.gpytorch_like_tridiag(op64, v0.double(), mc, dtype=torch.float64)
+    sc = float(refc["T"].abs().max())
+    floor = _rel(refc["T"], refc64["T"], sc)                                 # the fp32 oracle's own distance from fp64
+    resc = hlv.lanczos(op_gpu, mc, v0d, reorth="full", reorth_tol=1e-5)
+    assert sum(refc["extra_passes"]) > 0 and resc.conditional_passes > 0
+    assert _rel(resc.T, refc["T"], sc) < 1e-5 + floor and _rel(resc.T, refc64["T"], sc) < 1e-5 + floor
+    Qc = resc.Q.double()
+    assert float((Qc @ Qc.t() - torch.eye(mc, dtype=torch.float64, device=cuda_dev)).abs().max()) < 5e-6
+    # default (unconditional second pass) against the same oracle
+    ref = oracle.gpytorch_like_tridiag(lambda x: A @ x, v, m)
+    Q, T = hlv.lanczos_tridiag(closure, max_iter=m, dtype=torch.float32, device="cuda", matrix_shape=(n, n),
+                               init_vecs=v.to(cuda_dev).unsqueeze(1))
+    assert _rel(T, ref["T"], float(ref["T"].abs().max())) < 1e-5
+    # breakdown: 6 distinct eigenvalues, beta_6 < 1e-6 -> both stop at m' = 6
+    d = (centers * 1e-3).repeat_interleave(100)
+    dd = d.to(cuda_dev)
+    ref = oracle.gpytorch_like_tridiag(lambda x: d * x, v, 12)
+    Q, T = hlv.lanczos_tridiag(lambda q: dd.unsqueeze(1) * q, max_iter=12, dtype=torch.float32, device="cuda",
+                               matrix_shape=(n, n), init_vecs=v.to(cuda_dev).unsqueeze(1), check_every=1)
+    assert ref["m_eff"] == 6 and T.shape == (6, 6) and Q.shape == (n, 6)
+    assert _rel(torch.linalg.eigvalsh(T.double()), centers.double() * 1e-3, 1.3e-2) < 1e-5
+    # at most matrix_shape[-1] iterations, like gpytorch's num_iter = min(max_iter, P)
+    small = torch.diag(torch.tensor([1.0, 2.0, 4.0])).to(cuda_dev)
+    Q, T = hlv.lanczos_tridiag(lambda q: small @ q, max_iter=10, dtype=torch.float32, device="cuda", matrix_shape=(3, 3),
+                               init_vecs=torch.ones(3, 1, device=cuda_dev))
+    assert T.shape[0] <= 3
+
+
 # ---------------------------------------------------------------- HVP operators
 def _tiny_model(g):
     from transformers import GPT2Config, GPT2LMHeadModel

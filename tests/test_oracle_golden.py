@@ -249,3 +249,59 @@ def test_lowrank_adjust_against_real_reference_kernel():
         ref_native.vector_adjust_cpu(gvec, V, eig, adj, 1e-2)
         o = oracle.lowrank_adjust(torch.from_numpy(gvec), torch.from_numpy(V), torch.from_numpy(eig), 1e-2).numpy()
         assert np.abs(adj - o).max() <= 1e-5 * np.abs(o).max()
+
+
+# ---------------------------------------------------------------- gpytorch boundary (documentation-level oracle)
+def _planted(n, eigs, seed):
+    g = torch.Generator().manual_seed(seed)
+    U, _ = torch.linalg.qr(torch.randn(n, n, generator=g, dtype=torch.float64))
+    A = ((U * eigs.double()) @ U.t()).float()
+    return A, torch.randn(n, generator=g)
+
+
+def test_gpytorch_like_oracle_is_a_lanczos_tridiagonalisation():
+    """oracle.gpytorch_like_tridiag restates SURVEY Appendix B (PARITY UNPINNED: documentation, not source).  What CAN
+    be checked without gpytorch: it is a Lanczos tridiagonalisation (Q^T Q = I, Q^T A Q = T), T has max_iter rows
+    (First Principles Lanczos.ipynb cells 7-8: 10x10 against the hand loop's 11x11), the closure-facing order
+    "beta removed before alpha" agrees with the hand-loop order + CGS2 to rounding, and the start vector is normalised."""
+    n, m = 200, 10
+    torch.manual_seed(5)
+    A = torch.randn(n, n); A = (A + A.t()) / 2
+    v = torch.randn(n) * 3.0                                    # NOT normalised: the routine does it
+    r = oracle.gpytorch_like_tridiag(lambda x: A @ x, v, m)
+    Q, T = r["Q"].double(), r["T"].double()
+    assert Q.shape == (n, m) and T.shape == (m, m) and r["m_eff"] == m
+    assert float((Q.t() @ Q - torch.eye(m, dtype=torch.float64)).abs().max()) < 5e-6
+    scale = float(T.abs().max())
+    R = Q.t() @ A.double() @ Q - T
+    R[-1, -1] = 0.0
+    assert float(R.abs().max()) / scale < 2e-5
+    ref = oracle.lanczos_cgs2(lambda x: A @ x, v / v.norm(), m, reorth="full")
+    assert float((r["T"] - ref["T"]).abs().max()) / scale < 1e-5
+    assert sum(r["extra_passes"]) == 0                          # well-separated spectrum: the conditional passes never fire
+
+
+def test_gpytorch_like_oracle_conditional_passes_and_breakdown():
+    """The "while any q_i . r > tol" loop.  Measured here: with full reorthogonalisation of a SYMMETRIC operator in fp32
+    the projections after one Gram-Schmidt pass stay ~1e-7, so gpytorch's tol=1e-5 never fires -- not on clustered
+    spectra (6 clusters of width 1e-3 .. 1e-6), not at an exact invariant subspace; the branch is exercised with a tol at
+    the rounding level.  Breakdown: an operator with 6 distinct eigenvalues stops at m' = 6 when beta < 1e-6."""
+    n = 300
+    centers = torch.tensor([1.0, 2.0, 3.0, 5.0, 8.0, 13.0])
+    g = torch.Generator().manual_seed(9)
+    for width in (1e-3, 1e-6):
+        A, v = _planted(n, (centers[:, None] + width * torch.randn(6, 50, generator=g)).reshape(-1), seed=2)
+        r = oracle.gpytorch_like_tridiag(lambda x: A @ x, v, 12)
+        assert sum(r["extra_passes"]) == 0 and r["m_eff"] == 12
+    A, v = _planted(n, (centers[:, None] + 1e-3 * torch.randn(6, 50, generator=g)).reshape(-1), seed=2)
+    r = oracle.gpytorch_like_tridiag(lambda x: A @ x, v, 12, tol=1e-8)
+    assert sum(r["extra_passes"]) > 0                           # the loop ran ...
+    Q = r["Q"].double()
+    assert float((Q.t() @ Q - torch.eye(r["m_eff"], dtype=torch.float64)).abs().max()) < 5e-6   # ... and kept Q orthonormal
+    base = oracle.gpytorch_like_tridiag(lambda x: A @ x, v, 12)
+    assert float((r["T"][:6, :6] - base["T"][:6, :6]).abs().max()) / float(base["T"].abs().max()) < 1e-5
+    d = (centers * 1e-3).repeat_interleave(50)                   # exactly 6 distinct eigenvalues, small norm: beta_6 ~ 1e-9
+    r = oracle.gpytorch_like_tridiag(lambda x: d * x, v, 12)
+    assert r["m_eff"] == 6 and r["T"].shape == (6, 6)
+    ev = torch.linalg.eigvalsh(r["T"].double())
+    assert float((ev - centers.double() * 1e-3).abs().max()) < 1e-7
