@@ -391,10 +391,11 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats(dev)
 
+    first0 = getattr(run_dev, "first_replays", None)
     ms, launches, clocks, phases = timed(run_dev, e2e=False)
     value = args.steps / (ms / 1e3)
     peak_bytes = torch.cuda.max_memory_allocated(dev)
-    first_half_runs = getattr(run_dev, "first_replays", None)
+    first_half_runs = (run_dev.first_replays - first0) if first0 is not None else None
     ritz_top = None
     if real_run:
         res = eng.result()
@@ -443,12 +444,7 @@ def run_ours(args, rank, world, local_rank):
             del gop
             op_x.clear_cache()
             torch.cuda.empty_cache()
-            op_e = new_op(mine_dev, reuse)
-            ms_g, _, _, _ = timed(op_e, e2e=False)
-            extras["hvp_eager_no_cuda_graph"] = {"value": args.steps / (ms_g / 1e3), "ms_per_step": ms_g / args.steps,
-                                                 "note": "the headline policy issued from Python (no CUDA graph)"}
-            op_e.clear_cache()
-            del op_e, op_x
+            del op_x
             eng.hvp = op_dev
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
@@ -511,7 +507,7 @@ def run_ours(args, rank, world, local_rank):
             "hvp_ms_per_step": phases.get("hvp", {}).get("ms", 0.0) / args.steps,
             "phases_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in phases.items()},
             "hvp_policy": {"mode": args.hvp, "first_half_runs_in_timed_region": first_half_runs,
-                           "peak_device_bytes": peak_bytes, "kept_first_backward_graph_bytes": getattr(op_dev, "cached_bytes", None)},
+                           "peak_device_bytes": peak_bytes},
             "exchange": eng.exchange_mode,
             "hvp_mode": hvp_modes.get("value"), "ritz_top3": ritz_top, "extras": extras}
     # ---- CPU baseline: the reference's CPU path on this box's host cores (rank 0, N=1 only), a bounded sample ----

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhlv.so")
 
 HLV_OK = 0
-HLV_VERSION = 100          # must equal include/hlv.h's HLV_VERSION: a stale libhlv.so is refused at load
+HLV_VERSION = 200          # must equal include/hlv.h's HLV_VERSION: a stale libhlv.so is refused at load
 HLV_MAX_ROWS = 1024
 
 
@@ -20,6 +20,16 @@ class HLVError(RuntimeError):
     def __init__(self, fn: str, code: int, msg: str):
         super().__init__(f"{fn} failed with status {code}: {msg}")
         self.fn, self.code, self.msg = fn, code, msg
+
+
+HLV_MAX_PEERS = 16
+CH_HV, CH_ALPHA, CH_C1, CH_C2, CH_NORM, CH_V = 0, 1, 2, 3, 4, 5
+
+
+class PeerCtx(C.Structure):
+    """hlv_peer_ctx (include/hlv.h)."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("spin_timeout_ms", C.c_uint32), ("reserved", C.c_uint32),
+                ("xchg", C.c_void_p * HLV_MAX_PEERS)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -48,6 +58,20 @@ SIGNATURES = {
     "hlv_cgs_fused_max_rows": (C.c_int, [_i32]),
     "hlv_cgs_update_project_f32": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "hlv_cgs_update_project_bf16": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "hlv_peer_xchg_bytes": (_sz, []),
+    "hlv_peer_xchg_init": (C.c_int, [_vp, _vp]),
+    "hlv_peer_xchg_error": (C.c_int, [_vp, C.POINTER(C.c_int), _vp]),
+    "hlv_peer_signal": (C.c_int, [_vp, _i32, _vp]),
+    "hlv_peer_wait": (C.c_int, [_vp, _i32, _vp]),
+    "hlv_x_reduce_scatter_dot_f32": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hlv_x_update_project_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hlv_x_update_project_bf16": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hlv_x_lanczos_update_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "hlv_x_cgs_update_project_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "hlv_x_cgs_update_project_bf16": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "hlv_x_cgs_update_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "hlv_x_cgs_update_bf16": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "hlv_x_normalize_store_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _f64, _vp, _i32, _vp, _sz, _vp]),
     "hlv_vector_adjust_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _f32, _i64, _vp, _vp, _sz, _vp]),
     "hlv_ritz_vectors_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _i64, _vp]),
     "hlv_ritz_vectors_bf16": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _i64, _vp]),

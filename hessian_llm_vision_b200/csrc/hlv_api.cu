@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "hlv_common.cuh"
 
 namespace hlv {
@@ -48,6 +52,48 @@ int sm_count() {
     DevInfo d;
     if (query_device(&d) != HLV_OK) return 0;
     return d.sms;
+}
+
+static std::mutex g_cache_mu;
+static std::map<std::tuple<int, const void*, int, size_t>, int> g_occupancy;
+static std::map<std::pair<int, const void*>, size_t> g_smem_granted;
+
+int cached_occupancy(const void* func, int threads, size_t smem) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+    const auto key = std::make_tuple(dev, func, threads, smem);
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        auto it = g_occupancy.find(key);
+        if (it != g_occupancy.end()) return it->second;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        return 1;                                   // not cached: e.g. the shared-memory attribute was not raised yet
+    }
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    g_occupancy[key] = per_sm;
+    return per_sm;
+}
+
+cudaError_t ensure_dynamic_smem(const void* func, size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const auto key = std::make_pair(dev, func);
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        auto it = g_smem_granted.find(key);
+        if (it != g_smem_granted.end() && it->second >= smem) return cudaSuccess;
+    }
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    size_t& g = g_smem_granted[key];
+    if (g < smem) g = smem;
+    return cudaSuccess;
 }
 
 }  // namespace hlv

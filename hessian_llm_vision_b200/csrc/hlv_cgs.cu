@@ -10,7 +10,7 @@
 // past it, 8 fp32 / 16 bf16 rows (= 16 independent 128-bit loads per thread) at a time.
 // V is read exactly once per pass, w once (project) or once + one write (update).
 // Arithmetic intensity is 0.5 flop/byte (fp32 basis) -- HBM roofline, no tensor cores.
-#include "hlv_common.cuh"
+#include "hlv_peer.cuh"
 
 namespace hlv {
 
@@ -102,15 +102,33 @@ __device__ __forceinline__ void store_w(float* w_tile, int tid, int64_t valid, c
 
 // =============================================================================
 // project: c[i] = <V_i, w>
+// UPD: the three-term update  w -= alpha*vj + beta*vjm1  (lanczostrain_hand.py:202, torch's rounding sequence:
+// two products, one sum, one subtraction, no FMA contraction) is applied to the CTA's register slice of w first and
+// written back, then the rows are streamed past the UPDATED slice -- one launch and 12n bytes less than the separate
+// update kernel (v_j and v_{j-1} are rows of the basis that this pass reads anyway; they come back from L2).
+// With a peer view: alpha = rank-ordered total of HLV_CH_ALPHA, and the row totals of this rank are pushed on HLV_CH_C1.
 // =============================================================================
-template <typename BT>
+template <typename BT, bool UPD>
 __global__ void __launch_bounds__(kThreads, 2)
-cgs_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const float* __restrict__ w, int64_t n,
-                   double* partials, unsigned* counter, double* c_out) {
+cgs_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, float* __restrict__ w, int64_t n,
+                   const float* __restrict__ vj, const float* __restrict__ vjm1, double* alpha_p, const double* __restrict__ beta_p,
+                   double* partials, unsigned* counter, double* c_out, const __grid_constant__ PeerView pv, int push_channel) {
     extern __shared__ double s_acc[];                   // [kWarps][rows_pad]: per-warp running sums
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kRowBatch = row_batch<BT>();
     const int rows_pad = (rows + kRowBatch - 1) / kRowBatch * kRowBatch;
+    float alpha = 0.0f, beta = 0.0f;
+    if (UPD) {
+        double a;
+        if (pv.world > 1) {
+            a = peer_pull_scalar(pv, HLV_CH_ALPHA);
+            if (blockIdx.x == 0 && tid == 0) alpha_p[0] = a;      // the total, for the host's T
+        } else {
+            a = alpha_p[0];
+        }
+        alpha = (float)a;
+        beta = vjm1 != nullptr ? (float)beta_p[0] : 0.0f;
+    }
     for (int i = tid; i < kWarps * rows_pad; i += kThreads) s_acc[i] = 0.0;
     __syncthreads();
     double* my_acc = s_acc + warp * rows_pad;
@@ -121,6 +139,18 @@ cgs_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const float*
         const int64_t valid = n - x0;                   // >= kTile for every tile but a ragged last one
         float wv[8];
         load_w<BT>(w + x0, tid, valid, wv);
+        if (UPD) {
+            float a[8], b[8];
+            load_w<BT>(vj + x0, tid, valid, a);
+            if (vjm1 != nullptr) load_w<BT>(vjm1 + x0, tid, valid, b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float t = __fmul_rn(alpha, a[e]);
+                if (vjm1 != nullptr) t = __fadd_rn(t, __fmul_rn(beta, b[e]));
+                wv[e] = __fsub_rn(wv[e], t);
+            }
+            store_w<BT>(w + x0, tid, valid, wv);
+        }
         const BT* col0 = V + x0;
         for (int r0 = 0; r0 < rows; r0 += kRowBatch) {
             RowSlice<BT> s[kRowBatch];
@@ -156,7 +186,7 @@ cgs_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const float*
         for (int wi = 0; wi < kWarps; ++wi) t += s_acc[wi * rows_pad + r];
         partials[(size_t)r * kMaxCtas + blockIdx.x] = t;
     }
-    finalize_rows(partials, counter, rows, c_out);
+    finalize_rows_push(partials, counter, rows, c_out, pv, push_channel);
 }
 
 // =============================================================================
@@ -164,9 +194,9 @@ cgs_project_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const float*
 // =============================================================================
 template <typename BT>
 __global__ void __launch_bounds__(kThreads, 2)
-cgs_update_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const double* __restrict__ c, float sign,
+cgs_update_kernel(const BT* __restrict__ V, int64_t ldv, int rows, double* c, float sign,
                   float* __restrict__ w, int64_t n, double* partials, unsigned* counter, double* norm2_out,
-                  const int* __restrict__ run_flag) {
+                  const int* __restrict__ run_flag, const __grid_constant__ PeerView pv) {
     extern __shared__ float s_c[];                      // sign * (float)c[i]
     __shared__ double s_warp[kWarps];
     const int tid = threadIdx.x;
@@ -174,8 +204,13 @@ cgs_update_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const double*
     // w and norm2_out are left untouched and the ticket counter is not taken (every CTA leaves here)
     if (run_flag != nullptr && *run_flag == 0) return;
     constexpr int kRowBatch = row_batch<BT>();
-    for (int i = tid; i < rows; i += kThreads) s_c[i] = sign * (float)c[i];
-    __syncthreads();
+    if (pv.world > 1) {                                 // c = rank-ordered totals of the second projection
+        const bool keep = blockIdx.x == 0;
+        peer_pull(pv, HLV_CH_C2, rows, [&](int i, double t) { s_c[i] = sign * (float)t; if (keep) c[i] = t; });
+    } else {
+        for (int i = tid; i < rows; i += kThreads) s_c[i] = sign * (float)c[i];
+        __syncthreads();
+    }
     float nrm = 0.0f;
     const int64_t ntiles = (n + kTile - 1) / kTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -211,7 +246,7 @@ cgs_update_kernel(const BT* __restrict__ V, int64_t ldv, int rows, const double*
     if (norm2_out != nullptr) {
         double t = block_sum((double)nrm, s_warp);
         if (tid == 0) partials[blockIdx.x] = t;
-        finalize_rows(partials, counter, 1, norm2_out);
+        finalize_rows_push(partials, counter, 1, norm2_out, pv, HLV_CH_NORM);
     }
 }
 
@@ -309,41 +344,52 @@ static int check_basis(const char* name, const BT* V, int64_t ldv, int rows, con
     return HLV_OK;
 }
 
-template <typename BT>
-static int project(const char* name, const BT* V, int64_t ldv, int rows, const float* w, int64_t n,
+template <typename BT, bool UPD>
+static int project(const char* name, const hlv_peer_ctx* h_ctx, const BT* V, int64_t ldv, int rows, float* w, int64_t n,
+                   const float* vj, const float* vjm1, double* alpha, const double* beta,
                    double* c_out, void* ws_raw, size_t ws_bytes, cudaStream_t stream) {
     int rc = check_basis(name, V, ldv, rows, w, n);
     if (rc != HLV_OK) return rc;
+    if ((rc = check_peer_ctx(h_ctx, name)) != HLV_OK) return rc;
     HLV_REQUIRE(c_out != nullptr, HLV_ERR_ARG, "%s: c_out is NULL", name);
+    if (UPD) {
+        HLV_REQUIRE(vj && alpha && ((vjm1 == nullptr) == (beta == nullptr)), HLV_ERR_ARG,
+                    "%s: vj and alpha are required; vjm1 and beta go together", name);
+        HLV_REQUIRE(aligned16(vj) && aligned16(vjm1), HLV_ERR_ALIGN, "%s: vj, vjm1 must be 16-byte aligned", name);
+    }
     Workspace ws;
     HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, rows, &ws), HLV_ERR_WORKSPACE,
                 "%s: workspace too small for %d rows (need %zu bytes)", name, rows, workspace_bytes(rows));
     const int rows_pad = (rows + row_batch<BT>() - 1) / row_batch<BT>() * row_batch<BT>();
     const size_t smem = (size_t)kWarps * rows_pad * sizeof(double);
-    if (smem > 48 * 1024) {                             // only for rows > 768; per-device attribute
-        cudaError_t e = cudaFuncSetAttribute(cgs_project_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kWarps * (HLV_MAX_ROWS + 16) * (int)sizeof(double));
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(project)");
-    }
-    const int grid = persistent_grid((n + kTile - 1) / kTile, resident_ctas(cgs_project_kernel<BT>, smem));
-    cgs_project_kernel<BT><<<grid, kThreads, smem, stream>>>(V, ldv, rows, w, n, ws.partials, ws.counters, c_out);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(cgs_project_kernel<BT, UPD>),
+                                        smem > 48 * 1024 ? (size_t)kWarps * (HLV_MAX_ROWS + 16) * sizeof(double) : 0);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(project)");
+    const int grid = persistent_grid((n + kTile - 1) / kTile, resident_ctas(cgs_project_kernel<BT, UPD>, smem));
+    const PeerView pv = make_peer_view(h_ctx);
+    cgs_project_kernel<BT, UPD><<<grid, kThreads, smem, stream>>>(V, ldv, rows, w, n, vj, vjm1, alpha, beta, ws.partials, ws.counters,
+                                                                   c_out, pv, pv.world > 1 ? HLV_CH_C1 : -1);
     HLV_LAUNCH_CHECK(name);
     return HLV_OK;
 }
 
 template <typename BT>
-static int update(const char* name, const BT* V, int64_t ldv, int rows, const double* c, float sign, float* w,
+static int update(const char* name, const hlv_peer_ctx* h_ctx, const BT* V, int64_t ldv, int rows, double* c, float sign, float* w,
                   int64_t n, double* norm2_out, void* ws_raw, size_t ws_bytes, cudaStream_t stream,
                   const int* run_flag = nullptr) {
     int rc = check_basis(name, V, ldv, rows, w, n);
     if (rc != HLV_OK) return rc;
+    if ((rc = check_peer_ctx(h_ctx, name)) != HLV_OK) return rc;
     HLV_REQUIRE(c != nullptr, HLV_ERR_ARG, "%s: c is NULL", name);
+    const PeerView pv = make_peer_view(h_ctx);
+    HLV_REQUIRE(pv.world == 1 || (norm2_out != nullptr && run_flag == nullptr), HLV_ERR_ARG,
+                "%s: with a peer context the pass always runs and always reduces |w|^2", name);
     Workspace ws{};
     if (norm2_out)
         HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, 1, &ws), HLV_ERR_WORKSPACE, "%s: workspace too small", name);
     const int grid = persistent_grid((n + kTile - 1) / kTile, resident_ctas(cgs_update_kernel<BT>, rows * sizeof(float)));
     cgs_update_kernel<BT><<<grid, kThreads, rows * sizeof(float), stream>>>(V, ldv, rows, c, sign, w, n, ws.partials,
-                                                                           ws.counters, norm2_out, run_flag);
+                                                                           ws.counters, norm2_out, run_flag, pv);
     HLV_LAUNCH_CHECK(name);
     return HLV_OK;
 }
@@ -375,28 +421,30 @@ extern "C" {
 
 int hlv_cgs_project_f32(const float* V, int64_t ldv, int rows, const float* w, int64_t n, double* c_out,
                         void* ws, size_t ws_bytes, hlv_stream_t stream) {
-    return project<float>("hlv_cgs_project_f32", V, ldv, rows, w, n, c_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    return project<float, false>("hlv_cgs_project_f32", nullptr, V, ldv, rows, const_cast<float*>(w), n, nullptr, nullptr, nullptr, nullptr,
+                                 c_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int hlv_cgs_project_bf16(const uint16_t* V, int64_t ldv, int rows, const float* w, int64_t n, double* c_out,
                          void* ws, size_t ws_bytes, hlv_stream_t stream) {
-    return project<uint16_t>("hlv_cgs_project_bf16", V, ldv, rows, w, n, c_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    return project<uint16_t, false>("hlv_cgs_project_bf16", nullptr, V, ldv, rows, const_cast<float*>(w), n, nullptr, nullptr, nullptr, nullptr,
+                                    c_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int hlv_cgs_update_f32(const float* V, int64_t ldv, int rows, const double* c, float sign, float* w, int64_t n,
                        double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
-    return update<float>("hlv_cgs_update_f32", V, ldv, rows, c, sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    return update<float>("hlv_cgs_update_f32", nullptr, V, ldv, rows, const_cast<double*>(c), sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int hlv_cgs_update_bf16(const uint16_t* V, int64_t ldv, int rows, const double* c, float sign, float* w, int64_t n,
                         double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
-    return update<uint16_t>("hlv_cgs_update_bf16", V, ldv, rows, c, sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    return update<uint16_t>("hlv_cgs_update_bf16", nullptr, V, ldv, rows, const_cast<double*>(c), sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int hlv_cgs_update_if_f32(const float* V, int64_t ldv, int rows, const double* c, float sign, float* w, int64_t n,
                           double* norm2_out, const int* run_flag, void* ws, size_t ws_bytes, hlv_stream_t stream) {
-    return update<float>("hlv_cgs_update_if_f32", V, ldv, rows, c, sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream), run_flag);
+    return update<float>("hlv_cgs_update_if_f32", nullptr, V, ldv, rows, const_cast<double*>(c), sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream), run_flag);
 }
 int hlv_cgs_update_if_bf16(const uint16_t* V, int64_t ldv, int rows, const double* c, float sign, float* w, int64_t n,
                            double* norm2_out, const int* run_flag, void* ws, size_t ws_bytes, hlv_stream_t stream) {
-    return update<uint16_t>("hlv_cgs_update_if_bf16", V, ldv, rows, c, sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream), run_flag);
+    return update<uint16_t>("hlv_cgs_update_if_bf16", nullptr, V, ldv, rows, const_cast<double*>(c), sign, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream), run_flag);
 }
 int hlv_cgs_needs_pass(const double* c, int rows, const double* norm2, double tol, int* flag_out, hlv_stream_t stream) {
     HLV_REQUIRE(c && norm2 && flag_out && rows >= 1 && tol >= 0.0, HLV_ERR_ARG, "hlv_cgs_needs_pass: bad argument");
@@ -405,18 +453,39 @@ int hlv_cgs_needs_pass(const double* c, int rows, const double* norm2, double to
     return HLV_OK;
 }
 
+int hlv_x_update_project_f32(const hlv_peer_ctx* h_ctx, const float* V, int64_t ldv, int rows, float* w, int64_t n,
+                             const float* vj, const float* vjm1, double* alpha, const double* beta,
+                             double* c_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return project<float, true>("hlv_x_update_project_f32", h_ctx, V, ldv, rows, w, n, vj, vjm1, alpha, beta, c_out, ws, ws_bytes,
+                                static_cast<cudaStream_t>(stream));
+}
+int hlv_x_update_project_bf16(const hlv_peer_ctx* h_ctx, const uint16_t* V, int64_t ldv, int rows, float* w, int64_t n,
+                              const float* vj, const float* vjm1, double* alpha, const double* beta,
+                              double* c_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return project<uint16_t, true>("hlv_x_update_project_bf16", h_ctx, V, ldv, rows, w, n, vj, vjm1, alpha, beta, c_out, ws, ws_bytes,
+                                   static_cast<cudaStream_t>(stream));
+}
+int hlv_x_cgs_update_f32(const hlv_peer_ctx* h_ctx, const float* V, int64_t ldv, int rows, double* c, float* w, int64_t n,
+                         double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return update<float>("hlv_x_cgs_update_f32", h_ctx, V, ldv, rows, c, -1.0f, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+int hlv_x_cgs_update_bf16(const hlv_peer_ctx* h_ctx, const uint16_t* V, int64_t ldv, int rows, double* c, float* w, int64_t n,
+                          double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return update<uint16_t>("hlv_x_cgs_update_bf16", h_ctx, V, ldv, rows, c, -1.0f, w, n, norm2_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int hlv_vector_adjust_f32(const float* grad_vector, const float* V, const float* eigvals,
                           float* adjusted_grad_vector, int num_eigenvalues, int64_t vec_len, float delta,
                           int64_t ldv, double* coef_scratch, void* ws, size_t ws_bytes, hlv_stream_t stream) {
     HLV_REQUIRE(eigvals && coef_scratch && adjusted_grad_vector, HLV_ERR_ARG, "hlv_vector_adjust_f32: bad argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = project<float>("hlv_vector_adjust_f32/project", V, ldv, num_eigenvalues, grad_vector, vec_len,
-                            coef_scratch, ws, ws_bytes, s);
+    int rc = project<float, false>("hlv_vector_adjust_f32/project", nullptr, V, ldv, num_eigenvalues, const_cast<float*>(grad_vector), vec_len,
+                                   nullptr, nullptr, nullptr, nullptr, coef_scratch, ws, ws_bytes, s);
     if (rc != HLV_OK) return rc;
     adjust_coef_kernel<<<(num_eigenvalues + 127) / 128, 128, 0, s>>>(coef_scratch, eigvals, delta, num_eigenvalues,
                                                                      coef_scratch);
     HLV_LAUNCH_CHECK("hlv_vector_adjust_f32/coef");
-    return update<float>("hlv_vector_adjust_f32/update", V, ldv, num_eigenvalues, coef_scratch, 1.0f,
+    return update<float>("hlv_vector_adjust_f32/update", nullptr, V, ldv, num_eigenvalues, coef_scratch, 1.0f,
                          adjusted_grad_vector, vec_len, nullptr, ws, ws_bytes, s);
 }
 

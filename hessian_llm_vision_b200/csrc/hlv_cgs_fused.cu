@@ -23,7 +23,9 @@
 #include <limits.h>
 #include <stdlib.h>
 
-#include "hlv_common.cuh"
+#include <mutex>
+
+#include "hlv_peer.cuh"
 
 namespace hlv {
 
@@ -124,21 +126,11 @@ __host__ __device__ inline FusedSmem fused_layout(int rows, int tw, int elem_byt
     return L;
 }
 
-template <typename Kernel>
-static int resident_ctas_fused(Kernel kernel, size_t smem) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFusedThreads, smem) != cudaSuccess || per_sm < 1) {
-        (void)cudaGetLastError();
-        per_sm = 1;
-    }
-    return per_sm;
-}
-
 template <typename BT, int CPT>
 __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm)
-cgs_update_project_kernel(const __grid_constant__ CUtensorMap tmap, int rows, const double* __restrict__ c_in,
+cgs_update_project_kernel(const __grid_constant__ CUtensorMap tmap, int rows, double* c_in,
                           float* __restrict__ w, int64_t n, double* partials, unsigned* counter,
-                          double* c_out, double* norm2_out) {
+                          double* c_out, double* norm2_out, const __grid_constant__ PeerView pv) {
     constexpr int TW = kFusedConsumers * CPT;               // tile width = CPT boxes
     constexpr int kBoxElems = kGroup * kBoxCols;
     constexpr uint32_t kBoxBytes = kBoxElems * sizeof(BT);
@@ -163,9 +155,18 @@ cgs_update_project_kernel(const __grid_constant__ CUtensorMap tmap, int rows, co
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < ngroups * kGroup; i += kFusedThreads) {
-        s_c[i] = i < rows ? -(float)c_in[i] : 0.0f;
-        s_acc[i] = 0.0;
+    if (pv.world > 1) {                                 // c_in = rank-ordered totals of the first projection
+        const bool keep = blockIdx.x == 0;
+        peer_pull(pv, HLV_CH_C1, rows, [&](int i, double t) { s_c[i] = -(float)t; if (keep) c_in[i] = t; });
+        for (int i = tid; i < ngroups * kGroup; i += kFusedThreads) {
+            if (i >= rows) s_c[i] = 0.0f;
+            s_acc[i] = 0.0;
+        }
+    } else {
+        for (int i = tid; i < ngroups * kGroup; i += kFusedThreads) {
+            s_c[i] = i < rows ? -(float)c_in[i] : 0.0f;
+            s_acc[i] = 0.0;
+        }
     }
     __syncthreads();
 
@@ -329,6 +330,13 @@ cgs_update_project_kernel(const __grid_constant__ CUtensorMap tmap, int rows, co
             }
         }
     }
+    if (pv.world > 1) {                                 // push (c2[0..rows), |w'|^2) as ONE message on HLV_CH_C2
+        __syncthreads();                                // every warp is done with the partials: row 0's region is free
+        double* stage = partials;
+        for (int i = tid; i <= rows; i += kFusedThreads) stage[i] = i < rows ? c_out[i] : norm2_out[0];
+        __syncthreads();
+        peer_push(pv, HLV_CH_C2, stage, rows + 1);
+    }
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda).
@@ -388,27 +396,57 @@ static int pick_cpt(int rows) {
     return 0;
 }
 
+// The host encodes one CUtensorMap per (basis pointer, pitch, rows, n, element type); a Lanczos run asks for the same
+// ~100 maps on every restart, so the last few hundred are kept (direct-mapped, keyed by the arguments).
+struct MapKey {
+    const void* V; int64_t ldv, n; int rows, elem;
+    bool operator==(const MapKey& o) const { return V == o.V && ldv == o.ldv && n == o.n && rows == o.rows && elem == o.elem; }
+};
+struct MapEntry { MapKey key; CUtensorMap map; bool used; };
+static MapEntry g_maps[512];
+static std::mutex g_maps_mu;
+
+template <typename BT>
+static int basis_map(CUtensorMap* out, const BT* V, int64_t ldv, int rows, int64_t n, const char* name) {
+    const MapKey key{V, ldv, n, rows, (int)sizeof(BT)};
+    const size_t h = (reinterpret_cast<uintptr_t>(V) >> 8) * 1315423911u + (size_t)rows * 2654435761u + (size_t)n * 97 + (size_t)ldv * 31 + sizeof(BT);
+    MapEntry& e = g_maps[h % 512];
+    {
+        std::lock_guard<std::mutex> lock(g_maps_mu);
+        if (e.used && e.key == key) { *out = e.map; return HLV_OK; }
+    }
+    const int rc = make_basis_map<BT>(out, V, ldv, rows, n, name);
+    if (rc != HLV_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_maps_mu);
+    e.key = key; e.map = *out; e.used = true;
+    return HLV_OK;
+}
+
 template <typename BT, int CPT>
-static int launch_fused(const BT* V, int64_t ldv, int rows, const double* c_in, float* w, int64_t n, const Workspace& ws,
+static int launch_fused(const PeerView& pv, const BT* V, int64_t ldv, int rows, double* c_in, float* w, int64_t n, const Workspace& ws,
                         double* c_out, double* norm2_out, cudaStream_t stream, const char* name) {
     const size_t smem = fused_layout(rows, kFusedConsumers * CPT, (int)sizeof(BT)).total;
-    cudaError_t e = cudaFuncSetAttribute(cgs_update_project_kernel<BT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const void* fn = reinterpret_cast<const void*>(cgs_update_project_kernel<BT, CPT>);
+    cudaError_t e = ensure_dynamic_smem(fn, smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(update_project)");
     const int64_t tw = kFusedConsumers * CPT;
-    const int grid = persistent_grid((n + tw - 1) / tw, resident_ctas_fused(cgs_update_project_kernel<BT, CPT>, smem));
+    const int grid = persistent_grid((n + tw - 1) / tw, cached_occupancy(fn, kFusedThreads, smem));
     CUtensorMap map;
-    const int rc = make_basis_map<BT>(&map, V, ldv, rows, n, name);
+    const int rc = basis_map<BT>(&map, V, ldv, rows, n, name);
     if (rc != HLV_OK) return rc;
     cgs_update_project_kernel<BT, CPT><<<grid, kFusedThreads, smem, stream>>>(map, rows, c_in, w, n, ws.partials, ws.counters,
-                                                                              c_out, norm2_out);
+                                                                              c_out, norm2_out, pv);
     HLV_LAUNCH_CHECK(name);
     return HLV_OK;
 }
 
 template <typename BT>
-static int update_project(const char* name, const BT* V, int64_t ldv, int rows, const double* c_in, float* w, int64_t n,
+static int update_project(const char* name, const hlv_peer_ctx* h_ctx, const BT* V, int64_t ldv, int rows, double* c_in, float* w, int64_t n,
                           double* c_out, double* norm2_out, void* ws_raw, size_t ws_bytes, cudaStream_t stream) {
     HLV_REQUIRE(V && w && c_in && c_out && norm2_out && n >= 0 && rows >= 1, HLV_ERR_ARG, "%s: bad argument", name);
+    const int prc = check_peer_ctx(h_ctx, name);
+    if (prc != HLV_OK) return prc;
+    const PeerView pv = make_peer_view(h_ctx);
     HLV_REQUIRE(ldv >= n, HLV_ERR_ARG, "%s: ldv=%lld < n=%lld", name, (long long)ldv, (long long)n);
     HLV_REQUIRE(aligned16(V) && aligned16(w) && ((ldv * (int64_t)sizeof(BT)) & 15) == 0, HLV_ERR_ALIGN,
                 "%s: V, w must be 16-byte aligned and ldv*sizeof(elem) a multiple of 16", name);
@@ -423,10 +461,10 @@ static int update_project(const char* name, const BT* V, int64_t ldv, int rows, 
     HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "%s: no CUDA device", name);
     switch (cpt) {
         case 8:
-            if constexpr (sizeof(BT) == 2) return launch_fused<BT, 8>(V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
-        case 4: return launch_fused<BT, 4>(V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
-        case 2: return launch_fused<BT, 2>(V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
-        default: return launch_fused<BT, 1>(V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
+            if constexpr (sizeof(BT) == 2) return launch_fused<BT, 8>(pv, V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
+        case 4: return launch_fused<BT, 4>(pv, V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
+        case 2: return launch_fused<BT, 2>(pv, V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
+        default: return launch_fused<BT, 1>(pv, V, ldv, rows, c_in, w, n, ws, c_out, norm2_out, stream, name);
     }
 }
 
@@ -443,12 +481,22 @@ int hlv_cgs_fused_max_rows(int elem_bytes) {
 
 int hlv_cgs_update_project_f32(const float* V, int64_t ldv, int rows, const double* c_in, float* w, int64_t n,
                                double* c_out, double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
-    return update_project<float>("hlv_cgs_update_project_f32", V, ldv, rows, c_in, w, n, c_out, norm2_out, ws, ws_bytes,
+    return update_project<float>("hlv_cgs_update_project_f32", nullptr, V, ldv, rows, const_cast<double*>(c_in), w, n, c_out, norm2_out, ws, ws_bytes,
                                  static_cast<cudaStream_t>(stream));
 }
 int hlv_cgs_update_project_bf16(const uint16_t* V, int64_t ldv, int rows, const double* c_in, float* w, int64_t n,
                                 double* c_out, double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
-    return update_project<uint16_t>("hlv_cgs_update_project_bf16", V, ldv, rows, c_in, w, n, c_out, norm2_out, ws, ws_bytes,
+    return update_project<uint16_t>("hlv_cgs_update_project_bf16", nullptr, V, ldv, rows, const_cast<double*>(c_in), w, n, c_out, norm2_out, ws, ws_bytes,
+                                    static_cast<cudaStream_t>(stream));
+}
+int hlv_x_cgs_update_project_f32(const hlv_peer_ctx* h_ctx, const float* V, int64_t ldv, int rows, double* c_in, float* w, int64_t n,
+                                 double* c_out, double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return update_project<float>("hlv_x_cgs_update_project_f32", h_ctx, V, ldv, rows, c_in, w, n, c_out, norm2_out, ws, ws_bytes,
+                                 static_cast<cudaStream_t>(stream));
+}
+int hlv_x_cgs_update_project_bf16(const hlv_peer_ctx* h_ctx, const uint16_t* V, int64_t ldv, int rows, double* c_in, float* w, int64_t n,
+                                  double* c_out, double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return update_project<uint16_t>("hlv_x_cgs_update_project_bf16", h_ctx, V, ldv, rows, c_in, w, n, c_out, norm2_out, ws, ws_bytes,
                                     static_cast<cudaStream_t>(stream));
 }
 

@@ -70,16 +70,19 @@ int sm_count();                                  // cached per device, <=0 on fa
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// Resident CTAs per SM of `kernel` (kThreads threads, `smem` dynamic bytes) from the occupancy API, so a
-// persistent grid is exactly ONE resident wave: no second, under-filled wave and no tail.
+// Resident CTAs per SM of a kernel from the occupancy API, so a persistent grid is exactly ONE resident wave: no
+// second, under-filled wave and no tail.  The answer is cached per (device, kernel, threads, shared memory): the
+// query costs microseconds on the host and the recurrence issues ~6 launches per iteration.
+int cached_occupancy(const void* func, int threads, size_t smem);                      // hlv_api.cu
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when `smem` exceeds what was already granted on this device
+cudaError_t ensure_dynamic_smem(const void* func, size_t smem);                        // hlv_api.cu
+template <typename Kernel>
+inline int cached_resident_ctas(Kernel kernel, int threads, size_t smem) {
+    return cached_occupancy(reinterpret_cast<const void*>(kernel), threads, smem);
+}
 template <typename Kernel>
 inline int resident_ctas(Kernel kernel, size_t smem = 0) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) {
-        (void)cudaGetLastError();
-        per_sm = 1;
-    }
-    return per_sm;
+    return cached_occupancy(reinterpret_cast<const void*>(kernel), kThreads, smem);
 }
 
 // Persistent grid: one resident wave, capped by the amount of work.

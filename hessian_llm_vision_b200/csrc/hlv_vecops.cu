@@ -4,7 +4,7 @@
 // All of these are pure HBM streams (<= 0.5 flop/byte): 128-bit coalesced accesses,
 // several independent loads in flight per thread, persistent grids sized from the SM count,
 // fixed-order reductions with an fp64 final stage (hlv_common.cuh).
-#include "hlv_common.cuh"
+#include "hlv_peer.cuh"
 
 namespace hlv {
 
@@ -280,10 +280,17 @@ dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
 template <bool HAS_OLD>
 __global__ void __launch_bounds__(kThreads)
 lanczos_update_kernel(float* __restrict__ w, const float* __restrict__ vj, const float* __restrict__ vo,
-                      const double* __restrict__ alpha_p, const double* __restrict__ beta_p, int64_t n,
-                      double* partials, unsigned* counter, double* norm2_out) {
+                      double* alpha_p, const double* __restrict__ beta_p, int64_t n,
+                      double* partials, unsigned* counter, double* norm2_out, const __grid_constant__ PeerView pv) {
     __shared__ double s_warp[kWarps];
-    const float alpha = (float)alpha_p[0];
+    double alpha_d;
+    if (pv.world > 1) {                                   // alpha = rank-ordered total of the partial dot products
+        alpha_d = peer_pull_scalar(pv, HLV_CH_ALPHA);
+        if (blockIdx.x == 0 && threadIdx.x == 0) alpha_p[0] = alpha_d;
+    } else {
+        alpha_d = alpha_p[0];
+    }
+    const float alpha = (float)alpha_d;
     const float beta = HAS_OLD ? (float)beta_p[0] : 0.0f;
     auto f = [&](float wv, float a, float b) -> float {
         float t = __fmul_rn(alpha, a);
@@ -332,16 +339,31 @@ lanczos_update_kernel(float* __restrict__ w, const float* __restrict__ vj, const
     double s = ((double)acc[0] + (double)acc[1]) + ((double)acc[2] + (double)acc[3]);
     s = block_sum(s, s_warp);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
-    finalize_rows(partials, counter, 1, norm2_out);
+    finalize_rows_push(partials, counter, 1, norm2_out, pv, HLV_CH_NORM);
 }
 
 // beta = sqrt(norm2); v = w / beta (true division, as torch does); optional bf16 row copy.
-template <bool BF16>
+// With a peer view: norm2 = rank-ordered total of HLV_CH_NORM, and the normalised shard is ALSO stored into every
+// rank's full-length vector at shard_lo (plain peer stores: the all-gather of v_{j+1} without a collective launch);
+// when every CTA's stores are fenced at system scope the last CTA raises HLV_CH_V on every rank.
+struct VecTable {
+    float* v[HLV_MAX_PEERS];
+    int count;
+};
+template <bool BF16, bool PEER>
 __global__ void __launch_bounds__(kThreads)
-normalize_store_kernel(const float* __restrict__ w, const double* __restrict__ norm2, int64_t n,
+normalize_store_kernel(const float* __restrict__ w, double* norm2, int64_t n,
                        double* beta_out, float* __restrict__ v_out, uint16_t* __restrict__ row_bf16,
-                       double breakdown_tol, int* breakdown_iter, int iter) {
-    const double beta_d = sqrt(norm2[0]);
+                       double breakdown_tol, int* breakdown_iter, int iter,
+                       const __grid_constant__ PeerView pv, const __grid_constant__ VecTable vt, int64_t shard_lo, unsigned* counter) {
+    double n2;
+    if (PEER && pv.world > 1) {
+        n2 = peer_pull_scalar(pv, HLV_CH_NORM);
+        if (blockIdx.x == 0 && threadIdx.x == 0) norm2[0] = n2;
+    } else {
+        n2 = norm2[0];
+    }
+    const double beta_d = sqrt(n2);
     const float beta = (float)beta_d;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         beta_out[0] = beta_d;
@@ -355,6 +377,14 @@ normalize_store_kernel(const float* __restrict__ w, const double* __restrict__ n
         if (v_out != nullptr) {
             reinterpret_cast<float4*>(v_out)[2 * i] = x0;
             reinterpret_cast<float4*>(v_out)[2 * i + 1] = x1;
+        }
+        if (PEER) {
+#pragma unroll 4
+            for (int p = 0; p < vt.count; ++p) {
+                float4* dst = reinterpret_cast<float4*>(vt.v[p] + shard_lo);
+                dst[2 * i] = x0;
+                dst[2 * i + 1] = x1;
+            }
         }
         if (BF16) {
             __nv_bfloat162 p0 = __floats2bfloat162_rn(x0.x, x0.y), p1 = __floats2bfloat162_rn(x0.z, x0.w);
@@ -378,10 +408,22 @@ normalize_store_kernel(const float* __restrict__ w, const double* __restrict__ n
     if (t < n) {
         float x = __fdiv_rn(w[t], beta);
         if (v_out != nullptr) v_out[t] = x;
+        if (PEER)
+            for (int p = 0; p < vt.count; ++p) vt.v[p][shard_lo + t] = x;
         if (BF16) {
             __nv_bfloat16 h = __float2bfloat16_rn(x);
             row_bf16[t] = *reinterpret_cast<uint16_t*>(&h);
         }
+    }
+    if (PEER && pv.world > 1 && vt.count > 0) {
+        __shared__ unsigned s_ticket_n;
+        __threadfence_system();                            // this thread's peer stores are ordered before the ticket
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket_n = atomicInc(counter, gridDim.x - 1);
+        __syncthreads();
+        if (s_ticket_n != gridDim.x - 1) return;
+        __threadfence_system();
+        peer_push(pv, HLV_CH_V, nullptr, 0);
     }
 }
 
@@ -419,48 +461,89 @@ int hlv_dot_f32(const float* a, const float* b, int64_t n, double* out, void* ws
     return HLV_OK;
 }
 
-int hlv_lanczos_update_f32(float* w, const float* vj, const float* vjm1, const double* alpha,
-                           const double* beta, int64_t n, double* norm2_out, void* ws_raw, size_t ws_bytes,
-                           hlv_stream_t stream) {
-    HLV_REQUIRE(w && vj && alpha && norm2_out && n >= 0, HLV_ERR_ARG, "hlv_lanczos_update_f32: bad argument");
-    HLV_REQUIRE((vjm1 == nullptr) == (beta == nullptr), HLV_ERR_ARG,
-                "hlv_lanczos_update_f32: vjm1 and beta must both be set or both NULL");
-    HLV_REQUIRE(aligned16(w) && aligned16(vj) && aligned16(vjm1), HLV_ERR_ALIGN,
-                "hlv_lanczos_update_f32: vectors must be 16-byte aligned");
+static int lanczos_update_impl(const char* name, const hlv_peer_ctx* h_ctx, float* w, const float* vj, const float* vjm1, double* alpha,
+                               const double* beta, int64_t n, double* norm2_out, void* ws_raw, size_t ws_bytes, hlv_stream_t stream) {
+    HLV_REQUIRE(w && vj && alpha && norm2_out && n >= 0, HLV_ERR_ARG, "%s: bad argument", name);
+    HLV_REQUIRE((vjm1 == nullptr) == (beta == nullptr), HLV_ERR_ARG, "%s: vjm1 and beta must both be set or both NULL", name);
+    HLV_REQUIRE(aligned16(w) && aligned16(vj) && aligned16(vjm1), HLV_ERR_ALIGN, "%s: vectors must be 16-byte aligned", name);
+    int rc = check_peer_ctx(h_ctx, name);
+    if (rc != HLV_OK) return rc;
     Workspace ws;
-    HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, 1, &ws), HLV_ERR_WORKSPACE, "hlv_lanczos_update_f32: workspace too small");
-    HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "hlv_lanczos_update_f32: no CUDA device");
+    HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, 1, &ws), HLV_ERR_WORKSPACE, "%s: workspace too small", name);
+    HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "%s: no CUDA device", name);
     const int grid = persistent_grid((n / 4 + kThreads * kVecPerThread - 1) / (kThreads * kVecPerThread) + 1,
                                      vjm1 ? resident_ctas(lanczos_update_kernel<true>) : resident_ctas(lanczos_update_kernel<false>));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const PeerView pv = make_peer_view(h_ctx);
     if (vjm1)
-        lanczos_update_kernel<true><<<grid, kThreads, 0, s>>>(w, vj, vjm1, alpha, beta, n, ws.partials, ws.counters, norm2_out);
+        lanczos_update_kernel<true><<<grid, kThreads, 0, s>>>(w, vj, vjm1, alpha, beta, n, ws.partials, ws.counters, norm2_out, pv);
     else
-        lanczos_update_kernel<false><<<grid, kThreads, 0, s>>>(w, vj, nullptr, alpha, nullptr, n, ws.partials, ws.counters, norm2_out);
-    HLV_LAUNCH_CHECK("hlv_lanczos_update_f32 launch");
+        lanczos_update_kernel<false><<<grid, kThreads, 0, s>>>(w, vj, nullptr, alpha, nullptr, n, ws.partials, ws.counters, norm2_out, pv);
+    HLV_LAUNCH_CHECK(name);
+    return HLV_OK;
+}
+
+int hlv_lanczos_update_f32(float* w, const float* vj, const float* vjm1, const double* alpha,
+                           const double* beta, int64_t n, double* norm2_out, void* ws_raw, size_t ws_bytes,
+                           hlv_stream_t stream) {
+    return lanczos_update_impl("hlv_lanczos_update_f32", nullptr, w, vj, vjm1, const_cast<double*>(alpha), beta, n, norm2_out,
+                               ws_raw, ws_bytes, stream);
+}
+int hlv_x_lanczos_update_f32(const hlv_peer_ctx* h_ctx, float* w, const float* vj, const float* vjm1, double* alpha,
+                             const double* beta, int64_t n, double* norm2_out, void* ws_raw, size_t ws_bytes,
+                             hlv_stream_t stream) {
+    return lanczos_update_impl("hlv_x_lanczos_update_f32", h_ctx, w, vj, vjm1, alpha, beta, n, norm2_out, ws_raw, ws_bytes, stream);
+}
+
+static int normalize_store_impl(const char* name, const hlv_peer_ctx* h_ctx, const float* w, double* norm2, int64_t n, double* beta_out,
+                                float* v_out, uint16_t* row_bf16, float* const* h_v_full, int64_t shard_lo, double breakdown_tol,
+                                int* breakdown_iter, int iter, void* ws_raw, size_t ws_bytes, hlv_stream_t stream) {
+    HLV_REQUIRE(w && norm2 && beta_out && n >= 0, HLV_ERR_ARG, "%s: bad argument", name);
+    HLV_REQUIRE(w != v_out, HLV_ERR_ARG, "%s: v_out must not alias w", name);
+    int rc = check_peer_ctx(h_ctx, name);
+    if (rc != HLV_OK) return rc;
+    const PeerView pv = make_peer_view(h_ctx);
+    VecTable vt{};
+    if (pv.world > 1 && h_v_full != nullptr && (v_out || row_bf16)) {
+        HLV_REQUIRE(shard_lo >= 0 && (shard_lo & 3) == 0, HLV_ERR_ALIGN, "%s: shard_lo must be a non-negative multiple of 4", name);
+        for (int p = 0; p < pv.world; ++p) {
+            HLV_REQUIRE(h_v_full[p] != nullptr && aligned16(h_v_full[p]), HLV_ERR_ALIGN, "%s: full vector of rank %d NULL or unaligned", name, p);
+            vt.v[p] = h_v_full[p];
+        }
+        vt.count = pv.world;
+    }
+    if (!v_out && !row_bf16) n = 0;                     // beta only (last iteration: residual norm)
+    HLV_REQUIRE(aligned16(w) && aligned16(v_out) && aligned16(row_bf16), HLV_ERR_ALIGN, "%s: vectors must be 16-byte aligned", name);
+    HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "%s: no CUDA device", name);
+    Workspace ws{};
+    const bool peer = pv.world > 1;
+    if (peer) HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, 1, &ws), HLV_ERR_WORKSPACE, "%s: workspace too small", name);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t items = (n / 8 + kThreads * 2 - 1) / (kThreads * 2) + 1;
+#define HLV_NORM_LAUNCH(B, P)                                                                                          \
+    do {                                                                                                               \
+        const int grid = persistent_grid(items, resident_ctas(normalize_store_kernel<B, P>));                          \
+        normalize_store_kernel<B, P><<<grid, kThreads, 0, s>>>(w, norm2, n, beta_out, v_out, row_bf16, breakdown_tol,  \
+                                                               breakdown_iter, iter, pv, vt, shard_lo, ws.counters);   \
+    } while (0)
+    if (row_bf16) { if (peer) HLV_NORM_LAUNCH(true, true); else HLV_NORM_LAUNCH(true, false); }
+    else          { if (peer) HLV_NORM_LAUNCH(false, true); else HLV_NORM_LAUNCH(false, false); }
+#undef HLV_NORM_LAUNCH
+    HLV_LAUNCH_CHECK(name);
     return HLV_OK;
 }
 
 int hlv_normalize_store_f32(const float* w, const double* norm2, int64_t n, double* beta_out, float* v_out,
                             uint16_t* row_bf16, double breakdown_tol, int* breakdown_iter, int iter,
                             hlv_stream_t stream) {
-    HLV_REQUIRE(w && norm2 && beta_out && n >= 0, HLV_ERR_ARG, "hlv_normalize_store_f32: bad argument");
-    HLV_REQUIRE(w != v_out, HLV_ERR_ARG, "hlv_normalize_store_f32: v_out must not alias w");
-    if (!v_out && !row_bf16) n = 0;                     // beta only (last iteration: residual norm)
-    HLV_REQUIRE(aligned16(w) && aligned16(v_out) && aligned16(row_bf16), HLV_ERR_ALIGN,
-                "hlv_normalize_store_f32: vectors must be 16-byte aligned");
-    HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "hlv_normalize_store_f32: no CUDA device");
-    const int grid = persistent_grid((n / 8 + kThreads * 2 - 1) / (kThreads * 2) + 1,
-                                     row_bf16 ? resident_ctas(normalize_store_kernel<true>) : resident_ctas(normalize_store_kernel<false>));
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (row_bf16)
-        normalize_store_kernel<true><<<grid, kThreads, 0, s>>>(w, norm2, n, beta_out, v_out, row_bf16,
-                                                               breakdown_tol, breakdown_iter, iter);
-    else
-        normalize_store_kernel<false><<<grid, kThreads, 0, s>>>(w, norm2, n, beta_out, v_out, nullptr,
-                                                                breakdown_tol, breakdown_iter, iter);
-    HLV_LAUNCH_CHECK("hlv_normalize_store_f32 launch");
-    return HLV_OK;
+    return normalize_store_impl("hlv_normalize_store_f32", nullptr, w, const_cast<double*>(norm2), n, beta_out, v_out, row_bf16, nullptr, 0,
+                                breakdown_tol, breakdown_iter, iter, nullptr, 0, stream);
+}
+int hlv_x_normalize_store_f32(const hlv_peer_ctx* h_ctx, const float* w, double* norm2, int64_t n, double* beta_out, float* v_out,
+                              uint16_t* row_bf16, float* const* h_v_full, int64_t shard_lo, double breakdown_tol,
+                              int* breakdown_iter, int iter, void* ws, size_t ws_bytes, hlv_stream_t stream) {
+    return normalize_store_impl("hlv_x_normalize_store_f32", h_ctx, w, norm2, n, beta_out, v_out, row_bf16, h_v_full, shard_lo,
+                                breakdown_tol, breakdown_iter, iter, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

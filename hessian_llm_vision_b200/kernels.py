@@ -281,3 +281,116 @@ def ritz_vectors(Q: torch.Tensor, m: int, Y: torch.Tensor, out: torch.Tensor, n:
         _lib.call(f"hlv_ritz_vectors_{sfx}", p, ldq, int(m), _cuda(Y, torch.float32, "Y"), Y.stride(0), int(nvec),
                   out.data_ptr(), out.stride(0) if out.shape[0] > 1 else (max(out.shape[1], n) + 7) // 8 * 8, int(n), _stream())
     launch_count += (nvec + 7) // 8
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# exchange-aware entry points (hlv_x_*): the same kernels with the inter-rank exchange fused in.  ``peer`` is a
+# peer.PeerContext or None (single GPU: alpha / coefficients are read from the given device buffers as usual).
+# ---------------------------------------------------------------------------------------------------------------
+def _ctx(peer):
+    return None if peer is None else C.byref(peer.ctx)
+
+
+def peer_xchg_bytes() -> int:
+    return int(_lib.load().hlv_peer_xchg_bytes())
+
+
+def peer_xchg_init(xchg: torch.Tensor) -> None:
+    with torch.cuda.device(xchg.device):
+        _lib.call("hlv_peer_xchg_init", _cuda(xchg, torch.uint8, "xchg"), _stream())
+
+
+def peer_error(peer) -> int:
+    """0, or 1 + channel of a wait that ran into its time limit (synchronises)."""
+    err = C.c_int(0)
+    with torch.cuda.device(peer.xchg.device):
+        _lib.call("hlv_peer_xchg_error", peer.xchg.data_ptr(), C.byref(err), _stream())
+    return err.value
+
+
+def peer_signal(peer, channel: int) -> None:
+    global launch_count
+    with torch.cuda.device(peer.xchg.device):
+        _lib.call("hlv_peer_signal", _ctx(peer), int(channel), _stream())
+    launch_count += 1
+
+
+def peer_wait(peer, channel: int) -> None:
+    global launch_count
+    with torch.cuda.device(peer.xchg.device):
+        _lib.call("hlv_peer_wait", _ctx(peer), int(channel), _stream())
+    launch_count += 1
+
+
+def x_reduce_scatter_dot(peer, hv_ptrs, shard_lo: int, w: torch.Tensor, v: torch.Tensor, alpha_out: torch.Tensor,
+                         ws: Workspace) -> None:
+    """w = sum over ranks (rank order) of Hv_p[shard_lo : shard_lo + len(w)] read through peer memory;
+    alpha_out = <w, v> partial, pushed to every rank.  hv_ptrs: ctypes array of the ranks' full-length Hv buffers
+    as mapped in this process (or a 1-element array with the local pointer when peer is None)."""
+    global launch_count
+    n = w.numel()
+    with torch.cuda.device(w.device):
+        _lib.call("hlv_x_reduce_scatter_dot_f32", _ctx(peer), hv_ptrs, int(shard_lo), n, _cuda(w, torch.float32, "w"),
+                  _cuda(v, torch.float32, "v"), _cuda(alpha_out, torch.float64, "alpha_out"), ws.ptr, ws.nbytes, _stream())
+    launch_count += 1
+
+
+def x_update_project(peer, V: torch.Tensor, rows: int, w: torch.Tensor, vj: torch.Tensor, vjm1: Optional[torch.Tensor],
+                     alpha: torch.Tensor, beta: Optional[torch.Tensor], c_out: torch.Tensor, ws: Workspace) -> None:
+    """w -= alpha*vj + beta*vjm1 (lanczostrain_hand.py:202, torch's rounding) folded into the first projection
+    c_out = V[:rows] w_new; with peers alpha is the rank-ordered total and c_out is pushed."""
+    global launch_count
+    n = w.numel()
+    p, ldv, sfx = _basis(V, rows, n, "x_update_project")
+    if vj.numel() != n or (vjm1 is not None and vjm1.numel() != n):
+        raise ValueError("x_update_project: length mismatch")
+    with torch.cuda.device(w.device):
+        _lib.call(f"hlv_x_update_project_{sfx}", _ctx(peer), p, ldv, int(rows), _cuda(w, torch.float32, "w"), n,
+                  _cuda(vj, torch.float32, "vj"), _opt(vjm1, torch.float32, "vjm1"), _cuda(alpha, torch.float64, "alpha"),
+                  _opt(beta, torch.float64, "beta"), _cuda(c_out, torch.float64, "c_out"), ws.ptr, ws.nbytes, _stream())
+    launch_count += 1
+
+
+def x_lanczos_update(peer, w, vj, vjm1, alpha, beta, norm2_out, ws: Workspace) -> None:
+    global launch_count
+    n = w.numel()
+    with torch.cuda.device(w.device):
+        _lib.call("hlv_x_lanczos_update_f32", _ctx(peer), _cuda(w, torch.float32, "w"), _cuda(vj, torch.float32, "vj"),
+                  _opt(vjm1, torch.float32, "vjm1"), _cuda(alpha, torch.float64, "alpha"), _opt(beta, torch.float64, "beta"), n,
+                  _cuda(norm2_out, torch.float64, "norm2_out"), ws.ptr, ws.nbytes, _stream())
+    launch_count += 1
+
+
+def x_cgs_update_project(peer, V, rows: int, c_in, w, c_out, norm2_out, ws: Workspace) -> None:
+    global launch_count
+    n = w.numel()
+    p, ldv, sfx = _basis(V, rows, n, "x_cgs_update_project")
+    with torch.cuda.device(w.device):
+        _lib.call(f"hlv_x_cgs_update_project_{sfx}", _ctx(peer), p, ldv, int(rows), _cuda(c_in, torch.float64, "c_in"),
+                  _cuda(w, torch.float32, "w"), n, _cuda(c_out, torch.float64, "c_out"),
+                  _cuda(norm2_out, torch.float64, "norm2_out"), ws.ptr, ws.nbytes, _stream())
+    launch_count += 1
+
+
+def x_cgs_update(peer, V, rows: int, c, w, norm2_out, ws: Workspace) -> None:
+    global launch_count
+    n = w.numel()
+    p, ldv, sfx = _basis(V, rows, n, "x_cgs_update")
+    with torch.cuda.device(w.device):
+        _lib.call(f"hlv_x_cgs_update_{sfx}", _ctx(peer), p, ldv, int(rows), _cuda(c, torch.float64, "c"),
+                  _cuda(w, torch.float32, "w"), n, _cuda(norm2_out, torch.float64, "norm2_out"), ws.ptr, ws.nbytes, _stream())
+    launch_count += 1
+
+
+def x_normalize_store(peer, w, norm2, beta_out, v_out, row_bf16, v_full_ptrs, shard_lo: int, breakdown_tol: float,
+                      breakdown_iter, it: int, ws: Workspace) -> None:
+    """normalize_store with |w|^2 = the ranks' total; the normalised shard also goes straight into every rank's
+    full-length vector (v_full_ptrs) and HLV_CH_V is raised when it is on its way."""
+    global launch_count
+    n = w.numel()
+    with torch.cuda.device(w.device):
+        _lib.call("hlv_x_normalize_store_f32", _ctx(peer), _cuda(w, torch.float32, "w"), _cuda(norm2, torch.float64, "norm2"), n,
+                  _cuda(beta_out, torch.float64, "beta_out"), _opt(v_out, torch.float32, "v_out"),
+                  _opt(row_bf16, torch.bfloat16, "row_bf16"), v_full_ptrs, int(shard_lo), float(breakdown_tol),
+                  _opt(breakdown_iter, torch.int32, "breakdown_iter"), int(it), ws.ptr, ws.nbytes, _stream())
+    launch_count += 1

@@ -27,6 +27,7 @@ import torch
 
 from . import kernels as _kernels      # the CUDA library front end (raises at first use if libhlv.so is not built)
 from . import ritz as _ritz
+from ._lib import CH_HV as _CH_HV, CH_V as _CH_V
 
 _ALIGN = 8          # elements: keeps fp32 and bf16 rows 16-byte aligned
 
@@ -185,7 +186,7 @@ class LanczosEngine:
                  basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
                  breakdown_tol: Optional[float] = None, comm: Optional[Comm] = None,
                  profile: bool = False, column_vectors: bool = False, cgs_passes: int = 2, fused_cgs: bool = True,
-                 reorth_tol: Optional[float] = None, exchange: str = "auto"):
+                 reorth_tol: Optional[float] = None, exchange: str = "auto", peer=None):
         if reorth not in (None, "full"):
             raise ValueError("reorth must be None or 'full'")
         if basis_dtype not in (torch.float32, torch.bfloat16):
@@ -219,14 +220,9 @@ class LanczosEngine:
         if not self.fp32_rows:
             self.ring = [torch.zeros(sn, **f32) for _ in range(2)]
         # --- full-length buffers (only distinct from the shard when sharded) ---
-        if G > 1:
-            self.v_full = torch.zeros(self.n_pad, **f32)
-            self.hv_full = torch.zeros(self.n_pad, **f32)
-            self.w = torch.zeros(sn, **f32)
-        else:
-            self.v_full = None
-            self.hv_full = None
-            self.w = torch.zeros(sn, **f32)
+        self.v_full = None                                # allocated below, once the exchange mode is known
+        self.hv_full = None
+        self.w = torch.zeros(sn, **f32)
         # --- device scalars ---
         self.alphas = torch.zeros(m, **f64)
         self.betas = torch.zeros(m + 1, **f64)          # betas[j+1] = ||w|| after iteration j; betas[0] unused
@@ -254,11 +250,57 @@ class LanczosEngine:
             self.pass_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.pass_count = torch.zeros(1, dtype=torch.int32, device=self.device)    # iterations whose last pass was applied
             self.norm2_b = torch.zeros(1, **f64)
-        # how shards / coefficients move between ranks: "nccl" = torch.distributed collectives
+        # the three-term update folded into the first projection (hlv_x_update_project): one launch and one pass less
+        self.fold_update = self.reorth == "full" and hasattr(ops, "x_update_project")
+        # how shards / coefficients move between ranks: "nccl" = torch.distributed collectives; "peer" = inside the libhlv
+        # kernels over NVLink peer memory (csrc/hlv_peer.cuh)
         self.peer = None
+        self._v_pending = False
         self.exchange_mode = "none" if G == 1 else "nccl"
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        if G > 1 and exchange != "nccl":
+            why = self._peer_unsupported()
+            if why is None:
+                try:
+                    if peer is None:
+                        from . import peer as _peer
+                        peer = _peer.connect(self.comm, self.device, self.n_pad)
+                    self._adopt_peer(peer)
+                except Exception as e:  # noqa: BLE001 -- no symmetric memory on this system: keep the collectives
+                    why = f"{type(e).__name__}: {e}"
+            if self.peer is None:
+                if exchange == "peer":
+                    raise RuntimeError(f"exchange='peer' is not available: {why}")
+                self.exchange_mode = f"nccl (peer exchange unavailable: {str(why)[:200]})"
+        if G > 1 and self.peer is None:
+            self.v_full = torch.zeros(self.n_pad, **f32)
+            self.hv_full = torch.zeros(self.n_pad, **f32)
         self.j = 0
         self.launches = 0
+
+    def _peer_unsupported(self) -> Optional[str]:
+        """The fused exchange covers the default recurrences: no reorthogonalisation, or two-pass CGS with the fused
+        middle pass at every depth.  Anything else keeps the torch.distributed collectives."""
+        if getattr(self.comm, "backend", "nccl") == "gloo" or self.device.type != "cuda":
+            return "needs CUDA devices"
+        if not hasattr(self.ops, "x_reduce_scatter_dot"):
+            return "kernel front end has no exchange-aware entry points"
+        if self.reorth == "full" and not (self.fused and self.cgs_passes == 2 and self.m <= self.fused_max_rows):
+            return "needs the fused two-pass Gram-Schmidt path at every depth"
+        if self.reorth_tol is not None:
+            return "the conditional last pass is not exchange-aware"
+        if self.comm.world > 16:
+            return "more than 16 ranks"
+        return None
+
+    def _adopt_peer(self, peer) -> None:
+        if peer.world != self.comm.world or peer.rank != self.comm.rank or peer.hv_full.numel() < self.n_pad:
+            raise ValueError("peer context does not match this engine (world, rank, vector length)")
+        self.peer = peer
+        self.hv_full = peer.hv_full[: self.n_pad]
+        self.v_full = peer.v_full[: self.n_pad]
+        self.exchange_mode = "peer"
 
     # -- vectors ---------------------------------------------------------------
     def _v_shard(self, j: int) -> torch.Tensor:
@@ -295,18 +337,21 @@ class LanczosEngine:
             if self.keep_basis:
                 self.basis[0].copy_(local.to(self.basis_dtype))
         if self.comm.world > 1:
+            if self.peer is not None:
+                # run boundary: no rank may still be reading this rank's Hv (or writing its v) from the previous run
+                torch.cuda.synchronize(self.device)
+                self.comm.barrier()
+                self._v_pending = False
             self.v_full.zero_()
             self.v_full[: self.n].copy_(v0)
 
     # -- one operator application: fills self.w (local shard of H v_j) and alphas[j] ------
-    def _apply(self, j: int) -> None:
-        ops, G, n = self.ops, self.comm.world, self.n
+    def _hvp_into(self, j: int, target: torch.Tensor, fused_dot: bool) -> bool:
+        """target[:n] = (this rank's share of) H v_j.  Returns True when alphas[j] still has to be computed."""
+        ops, n, ph = self.ops, self.n, self.phases
         v_in = self._v_for_hvp(j)
         v_sh = self._v_shard(j)
         a_out = self.alphas[j: j + 1]
-        ph = self.phases
-        fused_dot = G == 1
-        target = self.w if G == 1 else self.hv_full
         tgt = target[:n] if target.numel() != n else target
         ph.start("hvp")
         if hasattr(self.hvp, "accumulate_into"):
@@ -315,62 +360,107 @@ class LanczosEngine:
             self.hvp.accumulate_into(v_in, tgt, dot_with=v_sh[:n] if fused_dot else None,
                                      dot_out=a_out if fused_dot else None, ws=self.ws, ops=ops, phases=ph)
             ph.stop("hvp")
-            need_dot = not fused_dot
-        else:
-            r = self.hvp(v_in)
-            ph.stop("hvp")
-            if isinstance(r, (list, tuple)):
-                ph.start("gather")
-                ops.gather(list(r), tgt, dot_with=v_sh[:n] if fused_dot else None,
-                           dot_out=a_out if fused_dot else None, ws=self.ws)
-                ph.stop("gather")
-                need_dot = not fused_dot
-            else:
-                r = r.detach().reshape(-1)
-                if r.numel() != n:
-                    raise ValueError(f"hvp returned {r.numel()} elements, expected {n}")
-                # always a copy into the engine's own w (4n bytes: 0.15 ms at GPT-2 size): an operator may return
-                # its input, a view of it, or a buffer it keeps -- w is updated in place by every kernel that follows
-                tgt.copy_(r)                                             # also converts dtype / device (a closure that ends in .cpu())
-                need_dot = True
+            return not fused_dot
+        r = self.hvp(v_in)
+        ph.stop("hvp")
+        if isinstance(r, (list, tuple)):
+            ph.start("gather")
+            ops.gather(list(r), tgt, dot_with=v_sh[:n] if fused_dot else None,
+                       dot_out=a_out if fused_dot else None, ws=self.ws)
+            ph.stop("gather")
+            return not fused_dot
+        r = r.detach().reshape(-1)
+        if r.numel() != n:
+            raise ValueError(f"hvp returned {r.numel()} elements, expected {n}")
+        # always a copy into the engine's own buffer (4n bytes: 0.15 ms at GPT-2 size): an operator may return its
+        # input, a view of it, or a buffer it keeps -- w is updated in place by every kernel that follows
+        tgt.copy_(r)                                                 # also converts dtype / device (a closure that ends in .cpu())
+        return True
+
+    def _apply(self, j: int):
+        """w = local shard of H v_j, alphas[j] = <w, v_j>: a generator (one yield per exchange point)."""
+        ops, G, ph, comm = self.ops, self.comm.world, self.phases, self.comm
+        v_sh = self._v_shard(j)
+        a_out = self.alphas[j: j + 1]
+        if self.peer is not None:
+            # peer exchange: wait until every rank's shard of v_j has landed in v_full, apply, tell the ranks, then read
+            # this rank's shard of every rank's Hv over NVLink (sum in rank order) with the alpha partial in the same pass
+            if self._v_pending:
+                ops.peer_wait(self.peer, _CH_V)
+                self._v_pending = False
+            self._hvp_into(j, self.hv_full, fused_dot=False)
+            ops.peer_signal(self.peer, _CH_HV)
+            yield
+            ph.start("reduce_scatter_alpha")
+            ops.x_reduce_scatter_dot(self.peer, self.peer.hv_ptrs, self.lo, self.w, v_sh, a_out, self.ws)
+            ph.stop("reduce_scatter_alpha")
+            yield
+            return
+        need_dot = self._hvp_into(j, self.w if G == 1 else self.hv_full, fused_dot=G == 1)
         if G > 1:
             ph.start("reduce_scatter")
-            self.comm.reduce_scatter_sum(self.w, self.hv_full)
+            comm.reduce_scatter_sum(self.w, self.hv_full)
             ph.stop("reduce_scatter")
         if need_dot:
             ph.start("dot")
             ops.dot(self.w, v_sh, a_out, self.ws)
             ph.stop("dot")
-            self.comm.all_reduce_sum(a_out)
+            comm.all_reduce_sum(a_out)
+        yield
 
     def step(self, j: Optional[int] = None, store_next: bool = True) -> None:
         """Iteration j of the hand loop (lanczostrain_hand.py:188-203 order):
         w = H v_j; alpha_j = w.v_j; w -= alpha_j v_j + beta_j v_{j-1}; [CGS2 vs rows 0..j];
         beta_{j+1} = ||w||; v_{j+1} = w / beta_{j+1}."""
+        for _ in self.step_phases(j, store_next):
+            pass
+
+    def step_phases(self, j: Optional[int] = None, store_next: bool = True):
+        """``step`` as a generator that yields after every launch whose result other ranks consume.  One rank per GPU
+        simply exhausts it; a single-GPU emulation of several ranks (tests) advances all ranks' generators in
+        lockstep, so that every push has been issued before the kernel that waits for it."""
         j = self.j if j is None else j
-        ops, ph, comm = self.ops, self.phases, self.comm
-        self._apply(j)
+        ops, ph, comm, peer = self.ops, self.phases, self.comm, self.peer
+        yield from self._apply(j)
         v_j = self._v_shard(j)
-        ph.start("update")
-        if j == 0:
-            ops.lanczos_update(self.w, v_j, None, self.alphas[j: j + 1], None, self.norm2, self.ws)
+        v_jm1 = self._v_shard(j - 1) if j > 0 else None
+        a_j = self.alphas[j: j + 1]
+        b_j = self.betas[j: j + 1] if j > 0 else None
+        x_path = peer is not None or self.fold_update          # hlv_x_* entry points (peer may be None: single GPU)
+        rows = j + 1
+        fused = self.reorth == "full" and self.fused and (peer is not None or self.fused_min_rows <= rows) and rows <= self.fused_max_rows
+        norm_reduced = peer is not None
+        if self.reorth != "full":
+            ph.start("update")
+            if x_path:
+                ops.x_lanczos_update(peer, self.w, v_j, v_jm1, a_j, b_j, self.norm2, self.ws)
+            else:
+                ops.lanczos_update(self.w, v_j, v_jm1, a_j, b_j, self.norm2, self.ws)
+            ph.stop("update")
+            yield
         else:
-            ops.lanczos_update(self.w, v_j, self._v_shard(j - 1), self.alphas[j: j + 1],
-                               self.betas[j: j + 1], self.norm2, self.ws)
-        ph.stop("update")
-        norm_reduced = False
-        if self.reorth == "full":
-            rows = j + 1
-            fused = self.fused and self.fused_min_rows <= rows <= self.fused_max_rows
             cur, nxt_c = self.coef, self.coef2
-            ph.start("cgs_project")
-            ops.cgs_project(self.basis, rows, self.w, cur, self.ws)
-            ph.stop("cgs_project", rows)
-            comm.all_reduce_sum(cur[:rows])
+            if x_path:          # three-term update folded into the first projection: one launch, one pass
+                ph.start("update_project")
+                ops.x_update_project(peer, self.basis, rows, self.w, v_j, v_jm1, a_j, b_j, cur, self.ws)
+                ph.stop("update_project", rows)
+            else:
+                ph.start("update")
+                ops.lanczos_update(self.w, v_j, v_jm1, a_j, b_j, self.norm2, self.ws)
+                ph.stop("update")
+                ph.start("cgs_project")
+                ops.cgs_project(self.basis, rows, self.w, cur, self.ws)
+                ph.stop("cgs_project", rows)
+            if peer is None:
+                comm.all_reduce_sum(cur[:rows])
+            yield
             for p in range(self.cgs_passes - 1):
                 if fused:           # update with c_p and project for c_{p+1} in ONE pass over the basis
                     ph.start("cgs_update_project")
-                    ops.cgs_update_project(self.basis, rows, cur, self.w, nxt_c, self.norm2, self.ws)
+                    if peer is not None:
+                        ops.x_cgs_update_project(peer, self.basis, rows, cur, self.w, nxt_c, self.norm2, self.ws)
+                    else:
+                        ops.cgs_update_project(self.basis, rows, cur, self.w, nxt_c, self.norm2, self.ws)
                     ph.stop("cgs_update_project", rows)
                 else:
                     ph.start("cgs_update")
@@ -379,8 +469,10 @@ class LanczosEngine:
                     ph.start("cgs_project")
                     ops.cgs_project(self.basis, rows, self.w, nxt_c, self.ws)
                     ph.stop("cgs_project", rows)
-                comm.all_reduce_sum(nxt_c[:rows])
+                if peer is None:
+                    comm.all_reduce_sum(nxt_c[:rows])
                 cur, nxt_c = nxt_c, cur
+                yield
             if self.reorth_tol is not None and fused:
                 # cur = V w' and norm2 = |w'|^2 were measured by the fused pass: is w' orthogonal enough already?
                 comm.all_reduce_sum(self.norm2)
@@ -395,8 +487,12 @@ class LanczosEngine:
                 norm_reduced = True
             else:
                 ph.start("cgs_update")
-                ops.cgs_update(self.basis, rows, cur, self.w, self.norm2, self.ws)
+                if peer is not None:
+                    ops.x_cgs_update(peer, self.basis, rows, cur, self.w, self.norm2, self.ws)
+                else:
+                    ops.cgs_update(self.basis, rows, cur, self.w, self.norm2, self.ws)
                 ph.stop("cgs_update", rows)
+            yield
         if not norm_reduced:
             comm.all_reduce_sum(self.norm2)
         if store_next:
@@ -407,14 +503,22 @@ class LanczosEngine:
                 row16 = self.basis[nxt] if (self.keep_basis and not self.fp32_rows) else None
             else:                       # last iteration: only beta_m (residual norm) is needed
                 v_out, row16 = None, None
-            ops.normalize_store(self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16,
-                                self.breakdown_tol, self.breakdown_iter, j)
+            if peer is not None:
+                ops.x_normalize_store(peer, self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16, peer.v_ptrs, self.lo,
+                                      self.breakdown_tol, self.breakdown_iter, j, self.ws)
+                self._v_pending = nxt < self.m
+            else:
+                ops.normalize_store(self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16,
+                                    self.breakdown_tol, self.breakdown_iter, j)
             ph.stop("normalize")
-            if comm.world > 1 and nxt < self.m:
+            if peer is None and comm.world > 1 and nxt < self.m:
                 ph.start("all_gather")
                 comm.all_gather(self.v_full, v_out)
                 ph.stop("all_gather")
+        elif peer is not None:
+            raise RuntimeError("store_next=False is not available with the peer exchange (the norm total is consumed by the normalise kernel)")
         self.j = j + 1
+        yield
 
     # -- checkpoint / resume ---------------------------------------------------------
     def state_dict(self, include_basis: bool = True) -> Dict[str, Any]:
@@ -467,6 +571,8 @@ class LanczosEngine:
         return a, b
 
     def result(self) -> LanczosResult:
+        if self.peer is not None and self.peer.error():
+            raise RuntimeError(f"peer exchange: a wait on channel {self.peer.error() - 1} ran into its time limit; results are invalid")
         bd = self.broke_down()
         m_eff = self.j if bd < 0 else min(self.j, bd + 1)
         a, b = self.tridiagonal(m_eff)

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define HLV_VERSION 100            /* 0.1.0 */
+#define HLV_VERSION 200            /* 0.2.0 */
 
 #define HLV_OK              0
 #define HLV_ERR_ARG        -1      /* null pointer / negative size / rows out of range */
@@ -55,6 +55,9 @@ extern "C" {
 
 #define HLV_MAX_ROWS      1024     /* max basis rows per project/update call */
 #define HLV_MAX_TENSORS   1024     /* max tensors per gather/scatter launch (longer lists are chunked) */
+
+#define HLV_MAX_PEERS       16     /* ranks of one NVLink domain that can exchange through peer memory */
+#define HLV_PEER_CHANNELS    8
 
 typedef void* hlv_stream_t;
 
@@ -148,6 +151,83 @@ int hlv_cgs_update_project_f32 (const float*    V, int64_t ldv, int rows, const 
 int hlv_cgs_update_project_bf16(const uint16_t* V, int64_t ldv, int rows, const double* c_in,
                                 float* w, int64_t n, double* c_out, double* norm2_out,
                                 void* ws, size_t ws_bytes, hlv_stream_t stream);
+
+/* ---- (e) multi-GPU: the exchange steps fused into the recurrence kernels over NVLink peer memory -------------
+ * The reference has one NCCL site (distributed_scratch.py:8) and otherwise DataParallel; the sharded path here
+ *  has three exchange steps per iteration: reduce-scatter of Hv, k-float reductions of alpha /
+ * Gram-Schmidt coefficients / |w|^2, all-gather of v_{j+1}.  With a peer context they are not collective launches:
+ *   - hlv_x_reduce_scatter_dot_f32 reads its shard of every rank's Hv through peer loads, adds in rank order, writes w
+ *     and the alpha partial in the same pass;
+ *   - a kernel that finishes a reduction pushes its partial sums into every rank's exchange area from its last CTA,
+ *     and the kernel that needs the totals adds the ranks' contributions (rank order, float64) in its prologue;
+ *   - hlv_x_normalize_store_f32 writes v_{j+1}'s shard straight into every rank's full-length vector.
+ * hlv_peer_ctx: world/rank and, for every rank p, the address of p's exchange area AS MAPPED IN THIS PROCESS
+ * (CUDA IPC / symmetric memory; xchg[rank] is the local one).  Each area is hlv_peer_xchg_bytes() bytes, zeroed once
+ * by its owner (hlv_peer_xchg_init) before any rank uses it.  One rank per GPU: the waits spin on the device.
+ * A NULL context (or world == 1) makes every hlv_x_* call the single-GPU operation.
+ * Channels (fixed by convention, one push + one pull per iteration each): */
+#define HLV_CH_HV      0   /* flag: this rank's full-length Hv is complete */
+#define HLV_CH_ALPHA   1   /* 1 value:  <w, v_j> partial */
+#define HLV_CH_C1      2   /* rows values: first projection */
+#define HLV_CH_C2      3   /* rows + 1 values: second projection and |w'|^2 */
+#define HLV_CH_NORM    4   /* 1 value: |w|^2 partial */
+#define HLV_CH_V       5   /* flag: this rank's shard of v_{j+1} has been written into every rank's vector */
+typedef struct hlv_peer_ctx {
+    int32_t  world, rank;
+    uint32_t spin_timeout_ms;            /* 0 = 20 s; a wait that runs out sets the area's error word */
+    uint32_t reserved;
+    void*    xchg[HLV_MAX_PEERS];
+} hlv_peer_ctx;
+size_t hlv_peer_xchg_bytes(void);
+int    hlv_peer_xchg_init(void* xchg_local, hlv_stream_t stream);
+/* error word of the local area (0 = ok, 1 + channel = a wait on that channel timed out); synchronises `stream` */
+int    hlv_peer_xchg_error(const void* xchg_local, int* h_error_out, hlv_stream_t stream);
+/* flag-only push / wait on a channel (HLV_CH_HV after the HVP, HLV_CH_V before it) */
+int    hlv_peer_signal(const hlv_peer_ctx* h_ctx, int channel, hlv_stream_t stream);
+int    hlv_peer_wait(const hlv_peer_ctx* h_ctx, int channel, hlv_stream_t stream);
+
+/* w[i] = sum_p hv_p[shard_lo + i] (p = 0..world-1 in order; h_hv[p] = rank p's full-length Hv as mapped here),
+ * alpha partial = <w, v> -> alpha_out[0] (local) and pushed on HLV_CH_ALPHA.  Waits for HLV_CH_HV first.
+ * With a NULL context: w = hv_0[shard_lo..], alpha_out = <w, v> (the total).  Replaces reduce_scatter + dot + all_reduce. */
+int hlv_x_reduce_scatter_dot_f32(const hlv_peer_ctx* h_ctx, const float* const* h_hv, int64_t shard_lo, int64_t n,
+                                 float* w, const float* v, double* alpha_out,
+                                 void* ws, size_t ws_bytes, hlv_stream_t stream);
+/* Three-term update folded into the first projection (lanczostrain_hand.py:202, then the first sweep of the
+ * reorthogonalisation): alpha = total of HLV_CH_ALPHA (NULL context: alpha[0] as given) and is stored to alpha[0];
+ * w -= alpha*vj + beta*vjm1 with torch's rounding sequence (vjm1/beta NULL on the first iteration); c_out = V w_new
+ * (local partial; pushed on HLV_CH_C1).  vj / vjm1 are fp32 vectors (rows of an fp32 basis, or the ring). */
+int hlv_x_update_project_f32 (const hlv_peer_ctx* h_ctx, const float*    V, int64_t ldv, int rows, float* w, int64_t n,
+                              const float* vj, const float* vjm1, double* alpha, const double* beta,
+                              double* c_out, void* ws, size_t ws_bytes, hlv_stream_t stream);
+int hlv_x_update_project_bf16(const hlv_peer_ctx* h_ctx, const uint16_t* V, int64_t ldv, int rows, float* w, int64_t n,
+                              const float* vj, const float* vjm1, double* alpha, const double* beta,
+                              double* c_out, void* ws, size_t ws_bytes, hlv_stream_t stream);
+/* hlv_lanczos_update_f32 with alpha pulled from HLV_CH_ALPHA and |w|^2 pushed on HLV_CH_NORM (no-reorth runs). */
+int hlv_x_lanczos_update_f32(const hlv_peer_ctx* h_ctx, float* w, const float* vj, const float* vjm1,
+                             double* alpha, const double* beta, int64_t n, double* norm2_out,
+                             void* ws, size_t ws_bytes, hlv_stream_t stream);
+/* hlv_cgs_update_project_*: c_in = totals of HLV_CH_C1 (stored back to c_in), c_out / norm2_out local partials pushed
+ * together on HLV_CH_C2. */
+int hlv_x_cgs_update_project_f32 (const hlv_peer_ctx* h_ctx, const float*    V, int64_t ldv, int rows, double* c_in,
+                                  float* w, int64_t n, double* c_out, double* norm2_out,
+                                  void* ws, size_t ws_bytes, hlv_stream_t stream);
+int hlv_x_cgs_update_project_bf16(const hlv_peer_ctx* h_ctx, const uint16_t* V, int64_t ldv, int rows, double* c_in,
+                                  float* w, int64_t n, double* c_out, double* norm2_out,
+                                  void* ws, size_t ws_bytes, hlv_stream_t stream);
+/* hlv_cgs_update_*: c = the first `rows` totals of HLV_CH_C2 (stored back to c), |w|^2 pushed on HLV_CH_NORM. */
+int hlv_x_cgs_update_f32 (const hlv_peer_ctx* h_ctx, const float*    V, int64_t ldv, int rows, double* c,
+                          float* w, int64_t n, double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream);
+int hlv_x_cgs_update_bf16(const hlv_peer_ctx* h_ctx, const uint16_t* V, int64_t ldv, int rows, double* c,
+                          float* w, int64_t n, double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream);
+/* hlv_normalize_store_f32 with norm2 = total of HLV_CH_NORM (stored back to norm2[0]); additionally the normalised
+ * shard is written to h_v_full[p] + shard_lo for every rank p (h_v_full[p] = rank p's full-length vector as mapped
+ * here; NULL list = no peer writes) and HLV_CH_V is pushed when all of it is on its way.  v_out / row_bf16 as in
+ * hlv_normalize_store_f32; with everything NULL only beta is produced (and nothing is pushed). */
+int hlv_x_normalize_store_f32(const hlv_peer_ctx* h_ctx, const float* w, double* norm2, int64_t n,
+                              double* beta_out, float* v_out, uint16_t* row_bf16,
+                              float* const* h_v_full, int64_t shard_lo,
+                              double breakdown_tol, int* breakdown_iter, int iter,
+                              void* ws, size_t ws_bytes, hlv_stream_t stream);
 
 /* ---- low-rank gradient adjustment: drop-in for vector_adjust.cu:2-15 -------- */
 /* adjusted[x] += sum_i (1/eig[i] - 1/(eig[i]+delta)) * (grad . V_i) * V[i*ldv + x].

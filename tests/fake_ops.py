@@ -111,3 +111,13 @@ def cgs_update_project(V, rows, c_in, w, c_out, norm2_out, ws):
 
 def ritz_vectors(Q, m, Y, out, n):
     out[:, :n] = Y[:m].t() @ Q[:m, :n].float()
+
+
+def x_update_project(peer, V, rows, w, vj, vjm1, alpha, beta, c_out, ws):
+    assert peer is None
+    a = alpha[0].float()
+    if vjm1 is None:
+        w -= a * vj
+    else:
+        w -= (a * vj + beta[0].float() * vjm1)
+    cgs_project(V, rows, w, c_out, ws)

@@ -44,7 +44,7 @@ def test_library_is_sm100a_with_lineinfo(libhlv):
 
 
 def test_version_workspace_and_arg_errors(libhlv):
-    assert libhlv.hlv_version() == 100
+    assert libhlv.hlv_version() == 200
     assert libhlv.hlv_workspace_bytes(1) >= 256 + 2048 * 8
     assert libhlv.hlv_workspace_bytes(100) - libhlv.hlv_workspace_bytes(99) == 2048 * 8
     # argument validation happens before any device work -> safe without a GPU

@@ -247,14 +247,18 @@ def test_lanczos_tridiag_shim_vs_gpytorch_like_oracle(hlv, cuda_dev):
     Ad = A.to(cuda_dev)
     closure = lambda q: Ad @ q
     ref = oracle.gpytorch_like_tridiag(lambda x: A @ x, v * 2.5, m)
+    ref64 = oracle.gpytorch_like_tridiag(lambda x: A.double() @ x, v.double() * 2.5, m, dtype=torch.float64)
     scale = float(ref["T"].abs().max())
+    # m = 24 runs past the 6 clusters: T is sensitive there and the fp32 oracle itself sits `floor` away from float64
+    floor = _rel(ref["T"], ref64["T"], scale)
     Q, T = hlv.lanczos_tridiag(closure, max_iter=m, dtype=torch.float32, device="cuda", matrix_shape=(n, n),
                                init_vecs=(v * 2.5).to(cuda_dev).unsqueeze(1), tol=1e-5, reorth_tol=1e-5)
     assert Q.shape == (n, m) and T.shape == (m, m)
-    assert _rel(T, ref["T"], scale) < 1e-5                                   # alpha/beta per iteration
+    assert _rel(T, ref["T"], scale) < 1e-5 + floor and _rel(T, ref64["T"], scale) < 1e-5 + floor    # alpha/beta per iteration
+    assert _rel(T[:6, :6], ref["T"][:6, :6], scale) < 1e-5                   # before the clusters are exhausted: no floor needed
     Qd = Q.double()
     assert float((Qd.t() @ Qd - torch.eye(m, dtype=torch.float64, device=cuda_dev)).abs().max()) < 5e-6
-    assert float((Q.cpu() - ref["Q"]).abs().max()) < 5e-4                    # same Lanczos vectors, same signs
+    assert float((Q[:, :6].cpu() - ref["Q"][:, :6]).abs().max()) < 5e-4      # same Lanczos vectors, same signs
     res = hlv.lanczos(closure, m, (v / v.norm()).to(cuda_dev), reorth="full", reorth_tol=1e-5)
     assert res.conditional_passes == 0 and sum(ref["extra_passes"]) == 0
     # cancelling operator: the conditional pass fires with gpytorch's own tol, on both sides
@@ -274,10 +278,9 @@ def test_lanczos_tridiag_shim_vs_gpytorch_like_oracle(hlv, cuda_dev):
     Qc = resc.Q.double()
     assert float((Qc @ Qc.t() - torch.eye(mc, dtype=torch.float64, device=cuda_dev)).abs().max()) < 5e-6
     # default (unconditional second pass) against the same oracle
-    ref = oracle.gpytorch_like_tridiag(lambda x: A @ x, v, m)
     Q, T = hlv.lanczos_tridiag(closure, max_iter=m, dtype=torch.float32, device="cuda", matrix_shape=(n, n),
-                               init_vecs=v.to(cuda_dev).unsqueeze(1))
-    assert _rel(T, ref["T"], float(ref["T"].abs().max())) < 1e-5
+                               init_vecs=(v * 2.5).to(cuda_dev).unsqueeze(1))
+    assert _rel(T, ref["T"], scale) < 1e-5 + floor and _rel(T, ref64["T"], scale) < 1e-5 + floor
     # breakdown: 6 distinct eigenvalues, beta_6 < 1e-6 -> both stop at m' = 6
     d = (centers * 1e-3).repeat_interleave(100)
     dd = d.to(cuda_dev)

@@ -1,0 +1,139 @@
+"""-m gpu: the exchange-aware kernels (hlv_x_*) -- the inter-rank exchange of the sharded recurrence fused into the
+kernels over peer memory -- with 2..8 ranks EMULATED on one GPU in lockstep (tests/peer_emulation.py), against the
+single-rank kernels and the CPU oracle; and the three-term update folded into the first projection."""
+import pytest
+import torch
+
+import oracle
+from tests import peer_emulation as emu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K(cuda_dev, libhlv):
+    from hessian_llm_vision_b200 import kernels
+    return kernels
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,n", [(1, 5), (2, 2048), (9, 10_007), (40, 300_001)])
+def test_update_folded_into_projection_is_bit_identical(K, cuda_dev, dtype, rows, n):
+    """hlv_x_update_project (no peers) == hlv_lanczos_update followed by hlv_cgs_project: the same rounding sequence
+    per element (torch's, lanczostrain_hand.py:202) and the same reduction tree, so w AND c are bit-identical."""
+    g = torch.Generator(device=cuda_dev).manual_seed(rows * 7 + n)
+    ld = (n + 7) // 8 * 8
+    V = (torch.randn(rows + 1, ld, device=cuda_dev, generator=g) / n ** 0.5).to(dtype)
+    vj = torch.randn(ld, device=cuda_dev, generator=g)[:n].contiguous()
+    vo = torch.randn(ld, device=cuda_dev, generator=g)[:n].contiguous()
+    w0 = torch.randn(ld, device=cuda_dev, generator=g)[:n].contiguous()
+    alpha = torch.tensor([0.73], dtype=torch.float64, device=cuda_dev)
+    beta = torch.tensor([1.9], dtype=torch.float64, device=cuda_dev)
+    ws = K.Workspace(cuda_dev, max_rows=rows + 1)
+    for old in (vo, None):
+        wa, wb = w0.clone(), w0.clone()
+        ca = torch.zeros(rows, dtype=torch.float64, device=cuda_dev)
+        cb = torch.zeros_like(ca)
+        nrm = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+        K.lanczos_update(wa, vj, old, alpha, beta if old is not None else None, nrm, ws)
+        K.cgs_project(V, rows, wa, ca, ws)
+        K.x_update_project(None, V, rows, wb, vj, old, alpha, beta if old is not None else None, cb, ws)
+        assert torch.equal(wa, wb) and torch.equal(ca, cb)
+        ref = w0 - (alpha.float() * vj + (beta.float() * old if old is not None else 0))
+        assert torch.equal(wa, ref)                                     # and both equal torch's elementwise result
+
+
+@pytest.mark.parametrize("world,n", [(2, 4096), (3, 10_007), (4, 100_003), (8, 65_536 + 24)])
+def test_reduce_scatter_dot_over_peer_pointers(K, cuda_dev, world, n):
+    """w = sum_p Hv_p[shard] in RANK order (bit-exact against the same float32 sums done by torch), alpha partials
+    pushed to every rank and pulled as the rank-ordered float64 total -- identical on all ranks."""
+    sn = (-(-n // world) + 7) // 8 * 8
+    n_pad = sn * world
+    ctxs = emu.make_contexts(world, n_pad, cuda_dev)
+    g = torch.Generator(device=cuda_dev).manual_seed(world)
+    for c in ctxs:
+        c.hv_full.copy_(torch.randn(n_pad, device=cuda_dev, generator=g))
+    v = torch.randn(n_pad, device=cuda_dev, generator=g)
+    ws = [K.Workspace(cuda_dev, max_rows=2) for _ in range(world)]
+    w = [torch.zeros(sn, device=cuda_dev) for _ in range(world)]
+    a_part = [torch.zeros(1, dtype=torch.float64, device=cuda_dev) for _ in range(world)]
+    for rep in range(3):                                               # several epochs through the same channels
+        for c in ctxs:
+            K.peer_signal(c, 0)
+        for r, c in enumerate(ctxs):
+            K.x_reduce_scatter_dot(c, c.hv_ptrs, r * sn, w[r], v[r * sn:(r + 1) * sn], a_part[r], ws[r])
+        total = torch.zeros(n_pad, device=cuda_dev)
+        for c in ctxs:                                                 # rank order, float32: what the kernel does
+            total = total + c.hv_full if c.rank else c.hv_full.clone()
+        for r in range(world):
+            assert torch.equal(w[r], total[r * sn:(r + 1) * sn])
+            exact = torch.dot(w[r].double(), v[r * sn:(r + 1) * sn].double())
+            assert abs(float(a_part[r]) - float(exact)) <= 1e-6 * float(w[r].norm() * v[r * sn:(r + 1) * sn].norm())
+        # consume the alpha channel: the folded update pulls the total; use a 1-row basis of zeros so only alpha matters
+        alphas = []
+        for r, c in enumerate(ctxs):
+            a = a_part[r].clone()
+            Vz = torch.zeros(1, sn, device=cuda_dev)
+            cz = torch.zeros(1, dtype=torch.float64, device=cuda_dev)
+            wz = torch.zeros(sn, device=cuda_dev)
+            K.x_update_project(c, Vz, 1, wz, v[r * sn:(r + 1) * sn].contiguous(), None, a, None, cz, ws[r])
+            alphas.append(a)
+        expect = sum(float(x) for x in a_part)                         # float64, rank order
+        assert all(float(a) == float(alphas[0]) for a in alphas)       # bit-identical on every rank
+        assert abs(float(alphas[0]) - expect) <= 1e-12 * max(1.0, abs(expect))
+    assert all(c.error() == 0 for c in ctxs)
+
+
+def _engines(hlv, world, n, m, cuda_dev, reorth, basis_dtype, parts):
+    sn = (-(-n // world) + 7) // 8 * 8
+    ctxs = emu.make_contexts(world, sn * world, cuda_dev)
+    engs = []
+    for r in range(world):
+        part = parts[r]
+        engs.append(hlv.LanczosEngine(lambda v, part=part: part(v), n, m, cuda_dev, reorth=reorth, basis_dtype=basis_dtype,
+                                      comm=emu.EmulatedComm(world, r), exchange="peer", peer=ctxs[r]))
+    return engs, ctxs
+
+
+@pytest.mark.parametrize("reorth,basis_dtype", [("full", torch.float32), ("full", torch.bfloat16), (None, torch.float32)])
+@pytest.mark.parametrize("world,n,m", [(2, 2000, 24), (4, 50_003, 30), (8, 20_000, 16)])
+def test_sharded_engine_over_emulated_peers(cuda_dev, libhlv, world, n, m, reorth, basis_dtype):
+    """The whole sharded iteration with the exchange fused into the kernels: `world` ranks (batch-sharded operator,
+    basis sharded along P) on one GPU in lockstep against (1) the single-rank engine on the summed operator and (2) the
+    CPU oracle.  alpha/beta must be BIT-identical on every rank (same partials added in the same order)."""
+    import hessian_llm_vision_b200 as hlv
+    g = torch.Generator(device=cuda_dev).manual_seed(17 * world + n)
+    d = [torch.randn(n, device=cuda_dev, generator=g) for _ in range(world)]        # H = diag(sum_r d_r) + rank-2 coupling
+    u = torch.randn(n, device=cuda_dev, generator=g) / n ** 0.5
+    parts = [(lambda v, dr=dr: dr * v + (u * torch.dot(u, v)) / world) for dr in d]
+    dsum = torch.stack(d).sum(0)
+    whole = lambda v: dsum * v + u * torch.dot(u, v)
+    v0 = torch.randn(n, device=cuda_dev, generator=g)
+    v0 /= v0.norm()
+    engs, ctxs = _engines(hlv, world, n, m, cuda_dev, reorth, basis_dtype, parts)
+    for e in engs:
+        assert e.exchange_mode == "peer"
+        e.start(v0)
+    for j in range(m):
+        emu.lockstep(engs, j)
+    res = [e.result() for e in engs]
+    assert all(c.error() == 0 for c in ctxs)
+    for r in res[1:]:
+        assert torch.equal(r.alphas, res[0].alphas) and torch.equal(r.betas, res[0].betas)
+    one = hlv.lanczos(whole, m, v0, reorth=reorth, basis_dtype=basis_dtype, keep_basis=True)
+    scale = float(one.T.abs().max())
+    tol = 1e-5 if reorth == "full" and basis_dtype == torch.float32 else 2e-3      # bf16 rows / no reorth: rounding is amplified
+    assert float((res[0].alphas - one.alphas).abs().max()) / scale < tol
+    assert float((res[0].betas - one.betas).abs().max()) / scale < tol
+    if reorth == "full" and basis_dtype == torch.float32:
+        dc, uc = dsum.double().cpu(), u.double().cpu()
+        ref = oracle.lanczos_cgs2(lambda q: dc * q + uc * torch.dot(uc, q), v0.double().cpu(), m, reorth="full", dtype=torch.float64)
+        assert float((res[0].alphas - ref["alphas"]).abs().max()) / scale < 1e-5
+        assert float((res[0].betas - ref["betas"]).abs().max()) / scale < 1e-5
+        sn = engs[0].shard_n
+        Q = torch.cat([r.Q[:, :sn] for r in res], dim=1)[:, :n].double()          # shards side by side = the full rows
+        assert float((Q @ Q.t() - torch.eye(m, dtype=torch.float64, device=cuda_dev)).abs().max()) < 5e-6
+        assert float((Q.float() - one.Q).abs().max()) < 1e-4
+    # every rank holds the full next vector, delivered by the peers' normalise kernels
+    for e in engs[1:]:
+        assert torch.equal(e.v_full, engs[0].v_full)
