@@ -247,7 +247,7 @@ def test_lanczos_tridiag_shim_vs_gpytorch_like_oracle_host_logic(cpu_double):
     assert float((res.T - ref["T"]).abs().max()) / scale < 1e-5 + floor
     assert float((res.T.double() - ref64["T"]).abs().max()) / scale < 1e-5 + floor
     G = res.Q.double() @ res.Q.double().t()
-    assert float((G - torch.eye(m, dtype=torch.float64)).abs().max()) < 5e-6
+    assert float((G - torch.eye(m, dtype=torch.float64)).abs().max()) < 1e-5      # the rule's own guarantee (tol)
     d = (torch.tensor([1.0, 2.0, 3.0, 5.0]) * 1e-3).repeat_interleave(40)
     _, v0 = _sym(21, 160)
     ref = oracle.gpytorch_like_tridiag(lambda x: d * x, v0, 9)

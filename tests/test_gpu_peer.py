@@ -137,3 +137,78 @@ def test_sharded_engine_over_emulated_peers(cuda_dev, libhlv, world, n, m, reort
     # every rank holds the full next vector, delivered by the peers' normalise kernels
     for e in engs[1:]:
         assert torch.equal(e.v_full, engs[0].v_full)
+
+
+# ---------------------------------------------------------------- real ranks (one process per GPU), when the box has them
+_WORKER = r"""
+import os, sys, json, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["HLV_ROOT"])
+import hessian_llm_vision_b200 as hlv
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", init_method="tcp://127.0.0.1:" + os.environ["HLV_PORT"], rank=rank, world_size=world,
+                        device_id=torch.device("cuda", rank))
+n, m = 1_000_003, 30
+torch.manual_seed(0)
+d = torch.randn(8, n) * 1.5; v = torch.randn(n); v0 = (v / v.norm()).cuda()
+per = 8 // world                                     # H = mean of 8 diagonal operators, dealt to the ranks
+mine = (d[rank * per:(rank + 1) * per].sum(0) / 8).cuda()
+out = {}
+for name, kw in (("nccl", dict(exchange="nccl")), ("peer", dict(exchange="peer")),
+                 ("peer_bf16", dict(exchange="peer", basis_dtype=torch.bfloat16)), ("nccl_bf16", dict(exchange="nccl", basis_dtype=torch.bfloat16)),
+                 ("peer_noreorth", dict(exchange="peer", reorth=None)), ("nccl_noreorth", dict(exchange="nccl", reorth=None))):
+    kw.setdefault("reorth", "full")
+    try:
+        eng = hlv.LanczosEngine(lambda q: mine * q, n, m, torch.device("cuda", rank), comm=hlv.Comm(), **kw)
+        eng.start(v0)
+        for j in range(m):
+            eng.step(j)
+        res = eng.result()
+        out[name] = {"T": res.T, "mode": eng.exchange_mode}
+        del eng
+    except Exception as e:
+        out[name] = {"error": repr(e)[:500]}
+    torch.cuda.synchronize(); dist.barrier()
+if rank == 0:
+    torch.save(out, os.environ["HLV_OUT"])
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_rank_count_invariance_nccl_and_peer_exchange(cuda_dev, libhlv, tmp_path, world):
+    """T from 1 / 2 / 4 / 8 ranks agrees to <= 1e-6 relative -- with the torch.distributed
+    collectives AND with the exchange fused into the kernels over NVLink peer memory (symmetric memory); the two
+    exchange paths must agree with each other to the same bar.  Skips below `world` GPUs."""
+    import hessian_llm_vision_b200 as hlv
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import os, socket, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    worker = tmp_path / "w.py"
+    worker.write_text(_WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = tmp_path / "T.pt"
+    procs = [subprocess.Popen([sys.executable, str(worker)],
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), HLV_ROOT=root, HLV_PORT=str(port), HLV_OUT=str(out)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(world)]
+    for p in procs:
+        o, _ = p.communicate(timeout=900)
+        assert p.returncode == 0, o.decode()[-3000:]
+    got = torch.load(out)
+    n, m = 1_000_003, 30
+    torch.manual_seed(0)
+    d = torch.randn(8, n) * 1.5
+    v = torch.randn(n)
+    v0 = (v / v.norm()).to(cuda_dev)
+    dm = (d.sum(0) / 8).to(cuda_dev)
+    for sfx, kw, tol in (("", dict(reorth="full"), 1e-6), ("_bf16", dict(reorth="full", basis_dtype=torch.bfloat16), 2e-4),
+                         ("_noreorth", dict(reorth=None), 2e-3)):
+        one = hlv.lanczos(lambda q: dm * q, m, v0, **kw)
+        scale = float(one.T.abs().max())
+        for mode in ("nccl", "peer"):
+            g = got[mode + sfx]
+            assert "error" not in g, (mode + sfx, g)
+            assert g["mode"].startswith(mode), (mode + sfx, g["mode"])
+            assert float((g["T"] - one.T).abs().max()) / scale < tol, (mode + sfx, world)
+        assert float((got["peer" + sfx]["T"] - got["nccl" + sfx]["T"]).abs().max()) / scale < tol
