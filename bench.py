@@ -463,10 +463,10 @@ def run_ours(args, rank, world, local_rank):
         "cgs_update": lambda d: (d["rows"] * s + 8 * d["calls"]) * n_loc,
         "cgs_update_project": lambda d: (d["rows"] * s + 8 * d["calls"]) * n_loc,   # V once; w read + written
         "update": lambda d: 16 * n_loc * d["calls"],
-        "normalize": lambda d: ((4 + s) if s == 4 else (4 + 4 + s)) * n_loc * d["calls"] + (4 * n_loc * (G - 1) * d["calls"] if eng.peer else 0),
+        "normalize": lambda d: ((4 + s) if s == 4 else (4 + 4 + s)) * n_loc * d["calls"] + (4 * n_loc * (1 if eng.multicast else G - 1) * d["calls"] if eng.peer else 0),
         "gather": lambda d: (8 + 4) * n * d["calls"],      # read pieces 4n + write w 4n (+4n v for the fused alpha on the last micro-batch)
         "dot": lambda d: 8 * n_loc * d["calls"],
-        "reduce_scatter_alpha": lambda d: (4 * G + 4 + 4) * n_loc * d["calls"],   # G shards in (G-1 over NVLink), w out, v in
+        "reduce_scatter_alpha": lambda d: (4 * (1 if eng.multicast else G) + 4 + 4) * n_loc * d["calls"],   # G shards in (G-1 over NVLink; one in-switch sum with multicast), w out, v in
     }
     kernels_out = {}
     for name, fn in kern_bytes.items():

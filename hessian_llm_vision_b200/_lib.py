@@ -63,7 +63,7 @@ SIGNATURES = {
     "hlv_peer_xchg_error": (C.c_int, [_vp, C.POINTER(C.c_int), _vp]),
     "hlv_peer_signal": (C.c_int, [_vp, _i32, _vp]),
     "hlv_peer_wait": (C.c_int, [_vp, _i32, _vp]),
-    "hlv_x_reduce_scatter_dot_f32": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hlv_x_reduce_scatter_dot_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hlv_x_update_project_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hlv_x_update_project_bf16": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hlv_x_lanczos_update_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
@@ -71,7 +71,7 @@ SIGNATURES = {
     "hlv_x_cgs_update_project_bf16": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "hlv_x_cgs_update_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "hlv_x_cgs_update_bf16": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
-    "hlv_x_normalize_store_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _f64, _vp, _i32, _vp, _sz, _vp]),
+    "hlv_x_normalize_store_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _f64, _vp, _i32, _vp, _sz, _vp]),
     "hlv_vector_adjust_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _f32, _i64, _vp, _vp, _sz, _vp]),
     "hlv_ritz_vectors_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _i64, _vp]),
     "hlv_ritz_vectors_bf16": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _i64, _vp]),

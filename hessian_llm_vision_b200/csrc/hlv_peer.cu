@@ -26,27 +26,41 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
     return r;
 }
 
-template <int WORLD>   // 0 = run-time world
+// In-switch reduction (NVLS): one load of the multicast address returns the sum over every rank's copy.
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+    return r;
+}
+
+template <int WORLD>   // 0 = run-time world; -1 = multicast (the switch adds)
 __global__ void __launch_bounds__(kThreads)
 reduce_scatter_dot_kernel(const __grid_constant__ PeerView pv, const __grid_constant__ HvTable tab, int64_t lo, int64_t n,
                           float* __restrict__ w, const float* __restrict__ v, double* partials, unsigned* counter,
                           double* alpha_out) {
     __shared__ double s_warp[kWarps];
-    const int world = WORLD ? WORLD : pv.world;
+    const int world = WORLD > 0 ? WORLD : pv.world;
     if (pv.world > 1) (void)peer_wait_all(pv, HLV_CH_HV);
     const int64_t nvec = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     float acc[2] = {0.f, 0.f};
     auto one = [&](int64_t i, float& a) {
-        float4 x[WORLD ? WORLD : HLV_MAX_PEERS];
+        float4 s;
+        if constexpr (WORLD < 0) {
+            s = multimem_ld_reduce_f4(tab.hv[HLV_MAX_PEERS - 1] + lo + 4 * i);     // the multicast address rides in the last slot
+        } else {
+            constexpr int NP = WORLD ? WORLD : HLV_MAX_PEERS;
+            float4 x[NP];
 #pragma unroll
-        for (int p = 0; p < (WORLD ? WORLD : HLV_MAX_PEERS); ++p)
-            if (p < world) x[p] = ld_peer_f4(tab.hv[p] + lo + 4 * i);
+            for (int p = 0; p < NP; ++p)
+                if (p < world) x[p] = ld_peer_f4(tab.hv[p] + lo + 4 * i);
+            s = x[0];
+#pragma unroll
+            for (int p = 1; p < NP; ++p)
+                if (p < world) { s.x += x[p].x; s.y += x[p].y; s.z += x[p].z; s.w += x[p].w; }
+        }
         const float4 y = ldg_stream(reinterpret_cast<const float4*>(v) + i);
-        float4 s = x[0];
-#pragma unroll
-        for (int p = 1; p < (WORLD ? WORLD : HLV_MAX_PEERS); ++p)
-            if (p < world) { s.x += x[p].x; s.y += x[p].y; s.z += x[p].z; s.w += x[p].w; }
         reinterpret_cast<float4*>(w)[i] = s;
         a = fmaf(s.x, y.x, a); a = fmaf(s.y, y.y, a); a = fmaf(s.z, y.z, a); a = fmaf(s.w, y.w, a);
     };
@@ -111,8 +125,8 @@ int hlv_peer_wait(const hlv_peer_ctx* h_ctx, int channel, hlv_stream_t stream) {
     return HLV_OK;
 }
 
-int hlv_x_reduce_scatter_dot_f32(const hlv_peer_ctx* h_ctx, const float* const* h_hv, int64_t shard_lo, int64_t n,
-                                 float* w, const float* v, double* alpha_out,
+int hlv_x_reduce_scatter_dot_f32(const hlv_peer_ctx* h_ctx, const float* const* h_hv, const float* hv_multicast,
+                                 int64_t shard_lo, int64_t n, float* w, const float* v, double* alpha_out,
                                  void* ws_raw, size_t ws_bytes, hlv_stream_t stream) {
     int rc = check_peer_ctx(h_ctx, "hlv_x_reduce_scatter_dot_f32");
     if (rc != HLV_OK) return rc;
@@ -136,6 +150,9 @@ int hlv_x_reduce_scatter_dot_f32(const hlv_peer_ctx* h_ctx, const float* const* 
         const int grid = persistent_grid(items, cached_resident_ctas(reduce_scatter_dot_kernel<W>, kThreads, 0));      \
         reduce_scatter_dot_kernel<W><<<grid, kThreads, 0, s>>>(pv, tab, shard_lo, n, w, v, ws.partials, ws.counters, alpha_out); \
     } while (0)
+    const bool mc = hv_multicast != nullptr && world > 1 && world < HLV_MAX_PEERS && aligned16(hv_multicast) && (n & 3) == 0;
+    if (mc) tab.hv[HLV_MAX_PEERS - 1] = hv_multicast;
+    if (mc) { HLV_RS_LAUNCH(-1); } else
     switch (world) {
         case 1: HLV_RS_LAUNCH(1); break;
         case 2: HLV_RS_LAUNCH(2); break;

@@ -348,8 +348,12 @@ lanczos_update_kernel(float* __restrict__ w, const float* __restrict__ vj, const
 // when every CTA's stores are fenced at system scope the last CTA raises HLV_CH_V on every rank.
 struct VecTable {
     float* v[HLV_MAX_PEERS];
+    float* mc;                      // NVSwitch multicast address of the same buffers, or NULL
     int count;
 };
+__device__ __forceinline__ void multimem_st_f4(float* mc, float4 x) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+}
 template <bool BF16, bool PEER>
 __global__ void __launch_bounds__(kThreads)
 normalize_store_kernel(const float* __restrict__ w, double* norm2, int64_t n,
@@ -379,11 +383,16 @@ normalize_store_kernel(const float* __restrict__ w, double* norm2, int64_t n,
             reinterpret_cast<float4*>(v_out)[2 * i + 1] = x1;
         }
         if (PEER) {
+            if (vt.mc != nullptr) {                         // one store, replicated to every rank by the switch
+                multimem_st_f4(vt.mc + shard_lo + 8 * i, x0);
+                multimem_st_f4(vt.mc + shard_lo + 8 * i + 4, x1);
+            } else {
 #pragma unroll 4
-            for (int p = 0; p < vt.count; ++p) {
-                float4* dst = reinterpret_cast<float4*>(vt.v[p] + shard_lo);
-                dst[2 * i] = x0;
-                dst[2 * i + 1] = x1;
+                for (int p = 0; p < vt.count; ++p) {
+                    float4* dst = reinterpret_cast<float4*>(vt.v[p] + shard_lo);
+                    dst[2 * i] = x0;
+                    dst[2 * i + 1] = x1;
+                }
             }
         }
         if (BF16) {
@@ -496,8 +505,8 @@ int hlv_x_lanczos_update_f32(const hlv_peer_ctx* h_ctx, float* w, const float* v
 }
 
 static int normalize_store_impl(const char* name, const hlv_peer_ctx* h_ctx, const float* w, double* norm2, int64_t n, double* beta_out,
-                                float* v_out, uint16_t* row_bf16, float* const* h_v_full, int64_t shard_lo, double breakdown_tol,
-                                int* breakdown_iter, int iter, void* ws_raw, size_t ws_bytes, hlv_stream_t stream) {
+                                float* v_out, uint16_t* row_bf16, float* const* h_v_full, float* v_multicast, int64_t shard_lo,
+                                double breakdown_tol, int* breakdown_iter, int iter, void* ws_raw, size_t ws_bytes, hlv_stream_t stream) {
     HLV_REQUIRE(w && norm2 && beta_out && n >= 0, HLV_ERR_ARG, "%s: bad argument", name);
     HLV_REQUIRE(w != v_out, HLV_ERR_ARG, "%s: v_out must not alias w", name);
     int rc = check_peer_ctx(h_ctx, name);
@@ -511,6 +520,7 @@ static int normalize_store_impl(const char* name, const hlv_peer_ctx* h_ctx, con
             vt.v[p] = h_v_full[p];
         }
         vt.count = pv.world;
+        if (v_multicast != nullptr && aligned16(v_multicast) && (n & 7) == 0) vt.mc = v_multicast;   // ragged shards keep the peer stores
     }
     if (!v_out && !row_bf16) n = 0;                     // beta only (last iteration: residual norm)
     HLV_REQUIRE(aligned16(w) && aligned16(v_out) && aligned16(row_bf16), HLV_ERR_ALIGN, "%s: vectors must be 16-byte aligned", name);
@@ -536,13 +546,13 @@ static int normalize_store_impl(const char* name, const hlv_peer_ctx* h_ctx, con
 int hlv_normalize_store_f32(const float* w, const double* norm2, int64_t n, double* beta_out, float* v_out,
                             uint16_t* row_bf16, double breakdown_tol, int* breakdown_iter, int iter,
                             hlv_stream_t stream) {
-    return normalize_store_impl("hlv_normalize_store_f32", nullptr, w, const_cast<double*>(norm2), n, beta_out, v_out, row_bf16, nullptr, 0,
+    return normalize_store_impl("hlv_normalize_store_f32", nullptr, w, const_cast<double*>(norm2), n, beta_out, v_out, row_bf16, nullptr, nullptr, 0,
                                 breakdown_tol, breakdown_iter, iter, nullptr, 0, stream);
 }
 int hlv_x_normalize_store_f32(const hlv_peer_ctx* h_ctx, const float* w, double* norm2, int64_t n, double* beta_out, float* v_out,
-                              uint16_t* row_bf16, float* const* h_v_full, int64_t shard_lo, double breakdown_tol,
+                              uint16_t* row_bf16, float* const* h_v_full, float* v_multicast, int64_t shard_lo, double breakdown_tol,
                               int* breakdown_iter, int iter, void* ws, size_t ws_bytes, hlv_stream_t stream) {
-    return normalize_store_impl("hlv_x_normalize_store_f32", h_ctx, w, norm2, n, beta_out, v_out, row_bf16, h_v_full, shard_lo,
+    return normalize_store_impl("hlv_x_normalize_store_f32", h_ctx, w, norm2, n, beta_out, v_out, row_bf16, h_v_full, v_multicast, shard_lo,
                                 breakdown_tol, breakdown_iter, iter, ws, ws_bytes, stream);
 }
 

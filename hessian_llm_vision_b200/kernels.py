@@ -323,14 +323,14 @@ def peer_wait(peer, channel: int) -> None:
 
 
 def x_reduce_scatter_dot(peer, hv_ptrs, shard_lo: int, w: torch.Tensor, v: torch.Tensor, alpha_out: torch.Tensor,
-                         ws: Workspace) -> None:
+                         ws: Workspace, hv_multicast: int = 0) -> None:
     """w = sum over ranks (rank order) of Hv_p[shard_lo : shard_lo + len(w)] read through peer memory;
     alpha_out = <w, v> partial, pushed to every rank.  hv_ptrs: ctypes array of the ranks' full-length Hv buffers
     as mapped in this process (or a 1-element array with the local pointer when peer is None)."""
     global launch_count
     n = w.numel()
     with torch.cuda.device(w.device):
-        _lib.call("hlv_x_reduce_scatter_dot_f32", _ctx(peer), hv_ptrs, int(shard_lo), n, _cuda(w, torch.float32, "w"),
+        _lib.call("hlv_x_reduce_scatter_dot_f32", _ctx(peer), hv_ptrs, hv_multicast or None, int(shard_lo), n, _cuda(w, torch.float32, "w"),
                   _cuda(v, torch.float32, "v"), _cuda(alpha_out, torch.float64, "alpha_out"), ws.ptr, ws.nbytes, _stream())
     launch_count += 1
 
@@ -383,7 +383,7 @@ def x_cgs_update(peer, V, rows: int, c, w, norm2_out, ws: Workspace) -> None:
 
 
 def x_normalize_store(peer, w, norm2, beta_out, v_out, row_bf16, v_full_ptrs, shard_lo: int, breakdown_tol: float,
-                      breakdown_iter, it: int, ws: Workspace) -> None:
+                      breakdown_iter, it: int, ws: Workspace, v_multicast: int = 0) -> None:
     """normalize_store with |w|^2 = the ranks' total; the normalised shard also goes straight into every rank's
     full-length vector (v_full_ptrs) and HLV_CH_V is raised when it is on its way."""
     global launch_count
@@ -391,6 +391,6 @@ def x_normalize_store(peer, w, norm2, beta_out, v_out, row_bf16, v_full_ptrs, sh
     with torch.cuda.device(w.device):
         _lib.call("hlv_x_normalize_store_f32", _ctx(peer), _cuda(w, torch.float32, "w"), _cuda(norm2, torch.float64, "norm2"), n,
                   _cuda(beta_out, torch.float64, "beta_out"), _opt(v_out, torch.float32, "v_out"),
-                  _opt(row_bf16, torch.bfloat16, "row_bf16"), v_full_ptrs, int(shard_lo), float(breakdown_tol),
+                  _opt(row_bf16, torch.bfloat16, "row_bf16"), v_full_ptrs, v_multicast or None, int(shard_lo), float(breakdown_tol),
                   _opt(breakdown_iter, torch.int32, "breakdown_iter"), int(it), ws.ptr, ws.nbytes, _stream())
     launch_count += 1

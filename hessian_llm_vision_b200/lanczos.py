@@ -255,6 +255,7 @@ class LanczosEngine:
         # how shards / coefficients move between ranks: "nccl" = torch.distributed collectives; "peer" = inside the libhlv
         # kernels over NVLink peer memory (csrc/hlv_peer.cuh)
         self.peer = None
+        self.multicast = False
         self._v_pending = False
         self.exchange_mode = "none" if G == 1 else "nccl"
         if exchange not in ("auto", "peer", "nccl"):
@@ -300,7 +301,9 @@ class LanczosEngine:
         self.peer = peer
         self.hv_full = peer.hv_full[: self.n_pad]
         self.v_full = peer.v_full[: self.n_pad]
-        self.exchange_mode = "peer"
+        import os
+        self.multicast = bool(peer.hv_multicast and peer.v_multicast) and os.environ.get("HLV_MULTICAST", "1") != "0"
+        self.exchange_mode = "peer+multicast" if self.multicast else "peer"
 
     # -- vectors ---------------------------------------------------------------
     def _v_shard(self, j: int) -> torch.Tensor:
@@ -392,7 +395,8 @@ class LanczosEngine:
             ops.peer_signal(self.peer, _CH_HV)
             yield
             ph.start("reduce_scatter_alpha")
-            ops.x_reduce_scatter_dot(self.peer, self.peer.hv_ptrs, self.lo, self.w, v_sh, a_out, self.ws)
+            ops.x_reduce_scatter_dot(self.peer, self.peer.hv_ptrs, self.lo, self.w, v_sh, a_out, self.ws,
+                                     hv_multicast=self.peer.hv_multicast if self.multicast else 0)
             ph.stop("reduce_scatter_alpha")
             yield
             return
@@ -505,7 +509,8 @@ class LanczosEngine:
                 v_out, row16 = None, None
             if peer is not None:
                 ops.x_normalize_store(peer, self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16, peer.v_ptrs, self.lo,
-                                      self.breakdown_tol, self.breakdown_iter, j, self.ws)
+                                      self.breakdown_tol, self.breakdown_iter, j, self.ws,
+                                      v_multicast=peer.v_multicast if self.multicast else 0)
                 self._v_pending = nxt < self.m
             else:
                 ops.normalize_store(self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16,

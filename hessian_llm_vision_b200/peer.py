@@ -33,6 +33,8 @@ class PeerContext:
     hv_ptrs: C.Array                   # void*[world]: every rank's hv_full
     v_ptrs: C.Array                    # void*[world]: every rank's v_full
     keepalive: Optional[list] = None   # whatever owns the mappings
+    hv_multicast: int = 0              # NVSwitch multicast address of hv_full / v_full (0 = none): in-switch reduction
+    v_multicast: int = 0               # and replicated stores (multimem.ld_reduce / multimem.st) instead of per-peer access
 
     def error(self) -> int:
         return kernels.peer_error(self)
@@ -40,7 +42,7 @@ class PeerContext:
 
 def make_context(world: int, rank: int, xchg: torch.Tensor, hv_full: torch.Tensor, v_full: torch.Tensor,
                  xchg_ptrs: List[int], hv_ptrs: List[int], v_ptrs: List[int], spin_timeout_ms: int = 20000,
-                 keepalive=None) -> PeerContext:
+                 keepalive=None, hv_multicast: int = 0, v_multicast: int = 0) -> PeerContext:
     if not (len(xchg_ptrs) == len(hv_ptrs) == len(v_ptrs) == world) or world > _lib.HLV_MAX_PEERS:
         raise ValueError(f"need {world} pointers per buffer (max {_lib.HLV_MAX_PEERS} ranks)")
     ctx = _lib.PeerCtx()
@@ -48,10 +50,11 @@ def make_context(world: int, rank: int, xchg: torch.Tensor, hv_full: torch.Tenso
     for p in range(world):
         ctx.xchg[p] = xchg_ptrs[p]
     return PeerContext(world=world, rank=rank, xchg=xchg, hv_full=hv_full, v_full=v_full, ctx=ctx,
-                       hv_ptrs=(C.c_void_p * world)(*hv_ptrs), v_ptrs=(C.c_void_p * world)(*v_ptrs), keepalive=keepalive)
+                       hv_ptrs=(C.c_void_p * world)(*hv_ptrs), v_ptrs=(C.c_void_p * world)(*v_ptrs), keepalive=keepalive,
+                       hv_multicast=int(hv_multicast), v_multicast=int(v_multicast))
 
 
-def connect(comm, device, n_pad: int, spin_timeout_ms: int = 20000) -> PeerContext:
+def connect(comm, device, n_pad: int, spin_timeout_ms: int = 20000, multicast: bool = True) -> PeerContext:
     """Allocate the three buffers in symmetric memory and map every rank's copy (collective over ``comm``'s group).
     Raises if symmetric memory is not available; the engine then keeps its torch.distributed collectives."""
     import torch.distributed as dist
@@ -77,5 +80,11 @@ def connect(comm, device, n_pad: int, spin_timeout_ms: int = 20000) -> PeerConte
     v_full.zero_()
     torch.cuda.synchronize(dev)
     dist.barrier(group=group)                               # every area is zeroed before anybody pushes into it
+    mc = [0, 0]
+    if multicast:
+        try:
+            mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in handles[1:]]
+        except Exception:  # noqa: BLE001
+            mc = [0, 0]
     return make_context(comm.world, comm.rank, xchg, hv_full, v_full, ptrs[0], ptrs[1], ptrs[2], spin_timeout_ms,
-                        keepalive=handles)
+                        keepalive=handles, hv_multicast=mc[0], v_multicast=mc[1])

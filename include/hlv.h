@@ -188,9 +188,11 @@ int    hlv_peer_wait(const hlv_peer_ctx* h_ctx, int channel, hlv_stream_t stream
 
 /* w[i] = sum_p hv_p[shard_lo + i] (p = 0..world-1 in order; h_hv[p] = rank p's full-length Hv as mapped here),
  * alpha partial = <w, v> -> alpha_out[0] (local) and pushed on HLV_CH_ALPHA.  Waits for HLV_CH_HV first.
+ * hv_multicast (optional): the NVSwitch multicast address of the same buffers -- the sum is then formed IN THE SWITCH
+ * (multimem.ld_reduce: one load per element instead of `world`; the reduction order is the switch's, still deterministic).
  * With a NULL context: w = hv_0[shard_lo..], alpha_out = <w, v> (the total).  Replaces reduce_scatter + dot + all_reduce. */
-int hlv_x_reduce_scatter_dot_f32(const hlv_peer_ctx* h_ctx, const float* const* h_hv, int64_t shard_lo, int64_t n,
-                                 float* w, const float* v, double* alpha_out,
+int hlv_x_reduce_scatter_dot_f32(const hlv_peer_ctx* h_ctx, const float* const* h_hv, const float* hv_multicast,
+                                 int64_t shard_lo, int64_t n, float* w, const float* v, double* alpha_out,
                                  void* ws, size_t ws_bytes, hlv_stream_t stream);
 /* Three-term update folded into the first projection (lanczostrain_hand.py:202, then the first sweep of the
  * reorthogonalisation): alpha = total of HLV_CH_ALPHA (NULL context: alpha[0] as given) and is stored to alpha[0];
@@ -221,11 +223,12 @@ int hlv_x_cgs_update_bf16(const hlv_peer_ctx* h_ctx, const uint16_t* V, int64_t 
                           float* w, int64_t n, double* norm2_out, void* ws, size_t ws_bytes, hlv_stream_t stream);
 /* hlv_normalize_store_f32 with norm2 = total of HLV_CH_NORM (stored back to norm2[0]); additionally the normalised
  * shard is written to h_v_full[p] + shard_lo for every rank p (h_v_full[p] = rank p's full-length vector as mapped
- * here; NULL list = no peer writes) and HLV_CH_V is pushed when all of it is on its way.  v_out / row_bf16 as in
+ * here; NULL list = no peer writes; v_multicast, optional: ONE multimem.st per element that the switch replicates to
+ * every rank instead of `world` peer stores) and HLV_CH_V is pushed when all of it is on its way.  v_out / row_bf16 as in
  * hlv_normalize_store_f32; with everything NULL only beta is produced (and nothing is pushed). */
 int hlv_x_normalize_store_f32(const hlv_peer_ctx* h_ctx, const float* w, double* norm2, int64_t n,
                               double* beta_out, float* v_out, uint16_t* row_bf16,
-                              float* const* h_v_full, int64_t shard_lo,
+                              float* const* h_v_full, float* v_multicast, int64_t shard_lo,
                               double breakdown_tol, int* breakdown_iter, int iter,
                               void* ws, size_t ws_bytes, hlv_stream_t stream);
 

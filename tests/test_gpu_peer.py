@@ -154,6 +154,7 @@ d = torch.randn(8, n) * 1.5; v = torch.randn(n); v0 = (v / v.norm()).cuda()
 per = 8 // world                                     # H = mean of 8 diagonal operators, dealt to the ranks
 mine = (d[rank * per:(rank + 1) * per].sum(0) / 8).cuda()
 out = {}
+os.environ["HLV_MULTICAST"] = os.environ.get("HLV_TEST_MULTICAST", "1")
 for name, kw in (("nccl", dict(exchange="nccl")), ("peer", dict(exchange="peer")),
                  ("peer_bf16", dict(exchange="peer", basis_dtype=torch.bfloat16)), ("nccl_bf16", dict(exchange="nccl", basis_dtype=torch.bfloat16)),
                  ("peer_noreorth", dict(exchange="peer", reorth=None)), ("nccl_noreorth", dict(exchange="nccl", reorth=None))):
@@ -202,7 +203,10 @@ def test_rank_count_invariance_nccl_and_peer_exchange(cuda_dev, libhlv, tmp_path
     v = torch.randn(n)
     v0 = (v / v.norm()).to(cuda_dev)
     dm = (d.sum(0) / 8).to(cuda_dev)
-    for sfx, kw, tol in (("", dict(reorth="full"), 1e-6), ("_bf16", dict(reorth="full", basis_dtype=torch.bfloat16), 2e-4),
+    # 1 rank vs `world` ranks: each rank rounds its partial products d_r * q to fp32 BEFORE they are added, so the operator
+    # itself differs at the 1e-7 level between rank counts and 30 Lanczos iterations amplify that to ~1e-6 (measured 1.2e-6 at
+    # 2 ranks); the two exchange paths at the SAME rank count see the same partials and differ only in summation order.
+    for sfx, kw, tol in (("", dict(reorth="full"), 5e-6), ("_bf16", dict(reorth="full", basis_dtype=torch.bfloat16), 2e-4),
                          ("_noreorth", dict(reorth=None), 2e-3)):
         one = hlv.lanczos(lambda q: dm * q, m, v0, **kw)
         scale = float(one.T.abs().max())
@@ -211,4 +215,4 @@ def test_rank_count_invariance_nccl_and_peer_exchange(cuda_dev, libhlv, tmp_path
             assert "error" not in g, (mode + sfx, g)
             assert g["mode"].startswith(mode), (mode + sfx, g["mode"])
             assert float((g["T"] - one.T).abs().max()) / scale < tol, (mode + sfx, world)
-        assert float((got["peer" + sfx]["T"] - got["nccl" + sfx]["T"]).abs().max()) / scale < tol
+        assert float((got["peer" + sfx]["T"] - got["nccl" + sfx]["T"]).abs().max()) / scale < (1e-6 if sfx == "" else tol)
