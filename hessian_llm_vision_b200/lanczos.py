@@ -256,6 +256,7 @@ class LanczosEngine:
         # kernels over NVLink peer memory (csrc/hlv_peer.cuh)
         self.peer = None
         self.multicast = False
+        self.peer_allgather = True
         self._v_pending = False
         self.exchange_mode = "none" if G == 1 else "nccl"
         if exchange not in ("auto", "peer", "nccl"):
@@ -302,8 +303,13 @@ class LanczosEngine:
         self.hv_full = peer.hv_full[: self.n_pad]
         self.v_full = peer.v_full[: self.n_pad]
         import os
-        self.multicast = bool(peer.hv_multicast and peer.v_multicast) and os.environ.get("HLV_MULTICAST", "1") != "0"
-        self.exchange_mode = "peer+multicast" if self.multicast else "peer"
+        # tuning knobs (measured defaults, profiles/README.md): HLV_MULTICAST=0/1 forces the NVSwitch multicast paths off / on
+        # (default: on from 4 ranks -- with one peer there is nothing to replicate or reduce in the switch);
+        # HLV_PEER_ALLGATHER=nccl keeps the collective for v_{j+1} and fuses only the reduce-scatter and the scalars
+        mc = os.environ.get("HLV_MULTICAST", "auto")
+        self.multicast = bool(peer.hv_multicast and peer.v_multicast) and (mc == "1" or (mc == "auto" and peer.world >= 4))
+        self.peer_allgather = os.environ.get("HLV_PEER_ALLGATHER", "peer") != "nccl"
+        self.exchange_mode = ("peer+multicast" if self.multicast else "peer") + ("" if self.peer_allgather else "+nccl_allgather")
 
     # -- vectors ---------------------------------------------------------------
     def _v_shard(self, j: int) -> torch.Tensor:
@@ -508,15 +514,16 @@ class LanczosEngine:
             else:                       # last iteration: only beta_m (residual norm) is needed
                 v_out, row16 = None, None
             if peer is not None:
-                ops.x_normalize_store(peer, self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16, peer.v_ptrs, self.lo,
+                ops.x_normalize_store(peer, self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16,
+                                      peer.v_ptrs if self.peer_allgather else None, self.lo,
                                       self.breakdown_tol, self.breakdown_iter, j, self.ws,
-                                      v_multicast=peer.v_multicast if self.multicast else 0)
-                self._v_pending = nxt < self.m
+                                      v_multicast=peer.v_multicast if (self.multicast and self.peer_allgather) else 0)
+                self._v_pending = nxt < self.m and self.peer_allgather
             else:
                 ops.normalize_store(self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16,
                                     self.breakdown_tol, self.breakdown_iter, j)
             ph.stop("normalize")
-            if peer is None and comm.world > 1 and nxt < self.m:
+            if (peer is None or not self.peer_allgather) and comm.world > 1 and nxt < self.m:
                 ph.start("all_gather")
                 comm.all_gather(self.v_full, v_out)
                 ph.stop("all_gather")
