@@ -93,6 +93,10 @@ def parse_args():
                     help="graph: the whole double-backward (forward, both backward passes, gather) is captured once into a CUDA "
                          "graph and replayed every iteration -- all of the work, none of the ~4,000 Python-issued launches; "
                          "eager: issue it from Python every iteration like the reference")
+    ap.add_argument("--workload", default="lanczos", choices=["lanczos", "ritz", "adjust"],
+                    help="lanczos: the headline (default).  ritz: materialise all 100 Ritz vectors V = Y^T Q of the m=100 GPT-2 run "
+                         "(gpt2_hessian_cpu.py:217); adjust: the low-rank gradient adjustment with k=100 pairs (vector_adjust.cu) -- "
+                         "kernel-only legs with their own roofline, N=1")
     ap.add_argument("--small", action="store_true", help="tiny model for a functional check of this script (NOT a benchmark)")
     return ap.parse_args()
 
@@ -532,6 +536,75 @@ def run_ours(args, rank, world, local_rank):
     emit(line)
 
 
+# --------------------------------------------------------------------------- kernel-only legs: Ritz vectors, adjustment
+def run_aux(args):
+    """Consumers of the basis after the run, at GPT-2 size, device-resident, CUDA events."""
+    import numpy as np
+    from hessian_llm_vision_b200 import kernels
+    from hessian_llm_vision_b200.adjust import adjust_gradient_implicit
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    n = 1 << 20 if args.small else 124_046_592
+    m = M_DEPTH
+    g = torch.Generator(device=dev).manual_seed(3)
+    Q = torch.empty(m, n, device=dev)
+    for r in range(m):
+        Q[r].normal_(generator=g).mul_(1.0 / n ** 0.5)
+    Yt, _ = torch.linalg.qr(torch.randn(m, m, device=dev, generator=g, dtype=torch.float64))
+    peak, peak_src = measured_peak()
+    clocks = ClockSampler(0)
+    reps, warm = max(args.steps if args.steps != M_DEPTH else 5, 1), max(args.warmup, 3)
+
+    def time_it(fn):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.start()
+        ev0.record()
+        for _ in range(reps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / reps, clocks.stop()
+    if args.workload == "ritz":
+        Y = Yt.float().contiguous()
+        out = torch.empty(m, n, device=dev)
+        l0 = kernels.launch_count
+        ms, ck = time_it(lambda: kernels.ritz_vectors(Q, m, Y, out, n))
+        launches = (kernels.launch_count - l0) // (reps + warm)
+        nb = (m * 4 + m * 4) * n                              # read Q once, write V once
+        ref = (Yt[:, :3].t() @ Q[:, : 1 << 16].double())
+        err = float((out[:3, : 1 << 16].double() - ref).abs().max() / ref.abs().max())
+        gbs = nb / (ms * 1e-3) / 1e9
+        line = {"metric": "ritz_vectors_all_m100_gpt2_124m_ms", "value": ms, "unit": "ms", "higher_is_better": False,
+                "roofline": {"bound": "hbm", "kernel": "hlv::ritz_vectors_tc_kernel (tcgen05 kind::tf32, 3xTF32)" if os.environ.get("HLV_RITZ_TC", "1") != "0"
+                             else "hlv::ritz_vectors_kernel<float> (CUDA cores, 8 vectors per pass)",
+                             "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "bytes_per_launch": nb, "traffic": None,
+                             "peak_source": peak_src, "bytes_model": "(m*4 + nvec*4)*n: Q read once, V written once",
+                             "tflops_fp32_equivalent": 2.0 * m * m * n / (ms * 1e-3) / 1e12},
+                "max_rel_err_vs_float64_sample": err}
+    else:
+        k = m
+        lam = torch.linspace(0.5, 20.0, k, device=dev)
+        gvec = torch.randn(n, device=dev, generator=g)
+        ws = kernels.Workspace(dev, max_rows=k + 1)
+        outv = gvec.clone()
+        l0 = kernels.launch_count
+        ms, ck = time_it(lambda: adjust_gradient_implicit(gvec, Q, m, Yt.cpu().numpy(), lam.cpu().numpy(), 0.1, ws=ws, out=outv))
+        launches = (kernels.launch_count - l0) // (reps + warm)
+        nb = (2 * k * 4 + 16) * n                              # project (k rows + g) and update (k rows + out read/write)
+        gbs = nb / (ms * 1e-3) / 1e9
+        line = {"metric": "lowrank_adjust_k100_gpt2_124m_ms", "value": ms, "unit": "ms", "higher_is_better": False,
+                "roofline": {"bound": "hbm", "kernel": "hlv::cgs_project_kernel<float> + hlv::cgs_update_kernel<float>", "achieved": gbs,
+                             "peak": peak, "unit": "GB/s", "frac": gbs / peak, "bytes_per_launch": nb / 2, "traffic": None, "peak_source": peak_src,
+                             "bytes_model": "(2*k*4 + 16)*n over the two passes (implicit form: g += Q^T (Y diag(s) Y^T) (Q g), no Ritz vectors formed)"}}
+    line.update({"n_gpus": 1, "steps": reps, "warmup": warm, "ms_per_step": ms, "scaling": "n/a", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                 "config": {"workload": f"{args.workload}: m = k = {m}, P = {n}, fp32 basis resident in HBM", "l2": "no flush: every pass streams >= 49 GB"},
+                 "gpu_launches": launches, "clocks": ck, "e2e": None})
+    emit(line)
+
+
 def main():
     args = parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -541,6 +614,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload != "lanczos":
+        if rank == 0:
+            run_aux(args)
         return
     if world > 1:
         torch.cuda.set_device(local_rank)

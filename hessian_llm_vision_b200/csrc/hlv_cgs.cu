@@ -394,6 +394,10 @@ static int update(const char* name, const hlv_peer_ctx* h_ctx, const BT* V, int6
     return HLV_OK;
 }
 
+// hlv_ritz_tc.cu: the tensor-core pass over the columns [0, n_main)
+int ritz_vectors_tc(const float* Q, int64_t ldq, int m, const float* Y, int ldy, int v0, int nvec, float* out, int64_t ldo,
+                    int64_t n, cudaStream_t stream, int64_t* n_main_out);
+
 template <typename BT>
 static int ritz_vectors(const char* name, const BT* Q, int64_t ldq, int m, const float* Y, int ldy, int nvec,
                         float* out, int64_t ldo, int64_t n, cudaStream_t stream) {
@@ -403,12 +407,28 @@ static int ritz_vectors(const char* name, const BT* Q, int64_t ldq, int m, const
     HLV_REQUIRE(aligned16(Q) && aligned16(out) && ((ldq * (int64_t)sizeof(BT)) & 15) == 0 && ((ldo * 4) & 15) == 0,
                 HLV_ERR_ALIGN, "%s: Q, out must be 16-byte aligned with 16-byte row pitch", name);
     HLV_REQUIRE(sm_count() > 0, HLV_ERR_NO_DEVICE, "%s: no CUDA device", name);
-    const int grid = persistent_grid((n + kTile - 1) / kTile, resident_ctas(ritz_vectors_kernel<BT>, (size_t)m * kNv * sizeof(float)));
-    for (int v0 = 0; v0 < nvec; v0 += kNv) {
-        const int nv = nvec - v0 < kNv ? nvec - v0 : kNv;
-        ritz_vectors_kernel<BT><<<grid, kThreads, (size_t)m * kNv * sizeof(float), stream>>>(Q, ldq, m, Y, ldy, v0, nv,
-                                                                                            out, ldo, n);
-        HLV_LAUNCH_CHECK(name);
+    // More than 8 vectors from an fp32 basis: ONE pass over Q on the tensor cores (3xTF32, hlv_ritz_tc.cu), up to 112 vectors
+    // per pass; the CUDA-core kernel below (8 vectors per pass over Q) keeps the ragged last < 128 columns, small requests
+    // and bf16 rows.
+    for (int v0 = 0; v0 < nvec;) {
+        int64_t n_main = 0;
+        int slice = nvec - v0 < 112 ? nvec - v0 : 112;
+        if (sizeof(BT) == 4 && slice > kNv) {
+            const int rc = ritz_vectors_tc(reinterpret_cast<const float*>(Q), ldq, m, Y, ldy, v0, slice, out, ldo, n, stream, &n_main);
+            if (rc != HLV_OK) return rc;
+        }
+        if (n_main == 0) slice = slice < kNv ? slice : kNv;                       // CUDA-core pass over everything: 8 at a time
+        if (n_main < n) {
+            const int64_t nt = n - n_main;
+            const int grid = persistent_grid((nt + kTile - 1) / kTile, resident_ctas(ritz_vectors_kernel<BT>, (size_t)m * kNv * sizeof(float)));
+            for (int u0 = v0; u0 < v0 + slice; u0 += kNv) {
+                const int nv = v0 + slice - u0 < kNv ? v0 + slice - u0 : kNv;
+                ritz_vectors_kernel<BT><<<grid, kThreads, (size_t)m * kNv * sizeof(float), stream>>>(Q + n_main, ldq, m, Y, ldy, u0, nv,
+                                                                                                    out + n_main, ldo, nt);
+                HLV_LAUNCH_CHECK(name);
+            }
+        }
+        v0 += slice;
     }
     return HLV_OK;
 }

@@ -322,6 +322,33 @@ def test_ritz_vectors(K, cuda_dev, dtype, m, nvec, n):
     assert float((out[:, :n].double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("m,nvec,n", [(100, 100, 128 * 300), (100, 100, 128 * 301 + 77), (104, 112, 128 * 150), (13, 9, 1000),
+                                      (128, 40, 128 * 64 + 5), (50, 16, 128), (100, 113, 128 * 40), (57, 100, 100_003)])
+def test_ritz_vectors_tensor_core_pass(K, cuda_dev, m, nvec, n):
+    """More than 8 Ritz vectors from an fp32 basis: ONE pass over Q on tcgen05 (kind::tf32, 3xTF32 split, accumulators in
+    TMEM) for the whole-128-column tiles, the CUDA-core kernel for the ragged tail -- against float64.  Y orthonormal
+    (eigenvectors of T), Q orthonormal rows: every output entry is a length-m dot product, error bar 3e-6 of the scale
+    (3xTF32 carries ~2^-21 per product; the CUDA-core kernel with fp32 FMAs is at ~1e-7)."""
+    Q, _ = _basis(m, n, cuda_dev, torch.float32, m + n)
+    g = torch.Generator(device=cuda_dev).manual_seed(m * 131 + nvec)
+    Yfull, _ = torch.linalg.qr(torch.randn(m, m, device=cuda_dev, generator=g, dtype=torch.float64))
+    pad = max(nvec - m, 0)                                       # nvec may exceed m in a kernel test (113 > 112: two slices)
+    Y = torch.cat([Yfull, torch.randn(m, pad, device=cuda_dev, generator=g, dtype=torch.float64)], dim=1)[:, :nvec].float().contiguous()
+    ld = (n + 7) // 8 * 8
+    out = torch.full((nvec, ld), float("nan"), device=cuda_dev)
+    K.ritz_vectors(Q, m, Y, out, n)
+    ref = Y.double().t() @ Q[:, :n].double()
+    scale = float(ref.abs().max())
+    err = float((out[:, :n].double() - ref).abs().max())
+    assert not torch.isnan(out[:, :n]).any()
+    assert err <= 3e-6 * scale, (err / scale)
+    assert torch.isnan(out[:, n:]).all()                         # nothing written past n
+    # the same call restricted to 8 vectors goes through the CUDA-core kernel: the two paths agree
+    out8 = torch.full((8, ld), float("nan"), device=cuda_dev)
+    K.ritz_vectors(Q, m, Y[:, :8].contiguous(), out8, n)
+    assert float((out8[:, :n] - out[:8, :n]).abs().max()) <= 3e-6 * scale
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("m,k,n", [(6, 6, 1000), (24, 5, 70_003)])
 def test_adjust_implicit_equals_explicit_ritz_vectors(K, cuda_dev, dtype, m, k, n):
