@@ -14,15 +14,19 @@
 // accumulation in TMEM.
 //
 // Warp roles (320 threads, one CTA per SM, persistent over tiles):
-//   warp 0      TMA producer: per stage four [16 rows x 32 columns] boxes of the tile (SWIZZLE_128B: exactly the canonical
-//               MN-major UMMA layout -- 8-row x 128-byte atoms), rows >= m arrive as zeros
-//   warps 2-5   split: read the landed fp32 stage, write q_hi back in place and q_lo into the second buffer (same swizzled
-//               addresses, so the split is layout-agnostic), fence.proxy.async, arrive
+//   warp 0      TMA producer: one [16 rows x 128 columns] box (8 KB, row-major as in HBM) per stage into a 3-deep ring;
+//               rows >= m arrive as zeros
+//   warps 2-5   transpose + split: the contraction runs over the ROWS of the tile, so the operand has to be K-major =
+//               "basis-row index contiguous".  Thread t owns column x = t of the tile: it reads its 16 values of the stage
+//               (conflict-free scalar loads), and writes q_hi / q_lo as four 16-byte core-matrix rows each (conflict-free
+//               128-bit stores) in the canonical K-major no-swizzle UMMA layout; fence.proxy.async; arrive.  (The hardware's
+//               own transposing path -- an MN-major tf32 descriptor over the TMA-swizzled tile -- returned zeros on this
+//               part in every descriptor variant tried, so the transpose is done in the pass that has to split anyway.)
 //   warp 1      MMA issuer (one elected lane): 3 tcgen05.mma per 8-row K atom, tcgen05.commit frees the stage for the
-//               producer; after the last atom of a tile a commit hands the accumulator to the epilogue.  Also owns the TMEM
+//               split warps; after the last atom of a tile a commit hands the accumulator to the epilogue.  Also owns the TMEM
 //               allocation (2 x 128 columns: the accumulator is double-buffered, so tile t+1 is multiplied while tile t drains)
 //   warps 6-9   epilogue: tcgen05.ld 32x32b (lane = column x of the tile), one coalesced 128-byte store per output row
-// Y (hi and lo, zero padded) is staged once per CTA in the K-major no-swizzle core-matrix layout.
+// Y (hi and lo, zero padded) is staged once per CTA in the same K-major no-swizzle core-matrix layout.
 #include <cuda.h>
 #include <limits.h>
 #include <stdlib.h>
@@ -33,8 +37,10 @@ namespace hlv {
 
 constexpr int kTcTileCols = 128;                 // UMMA M
 constexpr int kTcStageRows = 16;                 // two K atoms of 8 rows per pipeline stage
-constexpr int kTcStages = 6;
-constexpr int kTcStageBytes = kTcStageRows * kTcTileCols * 4;        // 8 KB (hi) + the same for lo
+constexpr int kTcStages = 3;                     // (hi, lo) operand stages between the split warps and the MMA issuer
+constexpr int kTcMaxRawStages = 12;              // raw tiles between the TMA producer and the split warps: as many as fit
+                                                 // (HBM latency x 44 GB/s per SM wants >= 48 KB of loads in flight per SM)
+constexpr int kTcStageBytes = kTcStageRows * kTcTileCols * 4;        // 8 KB (raw) / 8 KB (hi) + 8 KB (lo)
 constexpr int kTcThreads = 320;
 constexpr int kTcMaxN = 112;
 constexpr int kTcMaxM = 128;
@@ -95,53 +101,58 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo_byt
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32: D = F32, A = B = TF32, A MN-major, B K-major, M = 128.
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32: D = F32 (bits 4-5), A = B = TF32 (bits 7-9, 10-12),
+// both operands K-major (bits 15, 16 clear), N >> 3 in bits 17-22, M >> 4 in bits 24-28 (M = 128).
 __host__ __device__ inline uint32_t tc_idesc(int n_cols) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n_cols >> 3) << 17) | ((128u >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 struct RitzTcSmem {
-    size_t a_hi, a_lo, b_hi, b_lo, bars, tmem_slot, total;
+    size_t raw, a_hi, a_lo, b_hi, b_lo, bars, tmem_slot, total;
 };
-__host__ __device__ inline RitzTcSmem ritz_tc_layout(int kchunks_pad, int n_cols) {
+__host__ __device__ inline RitzTcSmem ritz_tc_layout(int kchunks_pad, int n_cols, int raw_stages) {
     RitzTcSmem L;
-    L.a_hi = 0;
-    L.a_lo = (size_t)kTcStages * kTcStageBytes;
-    L.b_hi = 2 * (size_t)kTcStages * kTcStageBytes;
+    L.raw = 0;
+    L.a_hi = (size_t)raw_stages * kTcStageBytes;
+    L.a_lo = L.a_hi + (size_t)kTcStages * kTcStageBytes;
+    L.b_hi = L.a_lo + (size_t)kTcStages * kTcStageBytes;
     const size_t b_bytes = (size_t)kchunks_pad * n_cols * 32;            // per K chunk: [2 halves][n_cols/8][8][4 floats]
     L.b_lo = L.b_hi + b_bytes;
     L.bars = L.b_lo + b_bytes;
-    L.tmem_slot = L.bars + (3 * kTcStages + 4) * sizeof(uint64_t);
+    L.tmem_slot = L.bars + (2 * kTcMaxRawStages + 2 * kTcStages + 4) * sizeof(uint64_t);
     L.total = L.tmem_slot + 16;
     return L;
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const float* __restrict__ Y, int ldy, int v0, int nvec,
-                       int n_cols, float* __restrict__ out, int64_t ldo, int64_t ntiles) {
+                       int n_cols, float* __restrict__ out, int64_t ldo, int64_t ntiles, int raw_stages) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // the 128-byte swizzle atoms must sit on 1024-byte boundaries of the shared-memory address space
+    // generous alignment of the carve-up (TMA destinations need 128 bytes, UMMA core matrices 16)
     unsigned char* smem = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
     const int kchunks = (m + 7) / 8;
     const int nstages_per_tile = (kchunks + 1) / 2;
     const int kchunks_pad = 2 * nstages_per_tile;
-    const RitzTcSmem L = ritz_tc_layout(kchunks_pad, n_cols);
+    const RitzTcSmem L = ritz_tc_layout(kchunks_pad, n_cols, raw_stages);
+    unsigned char* raw = smem + L.raw;
     unsigned char* a_hi = smem + L.a_hi;
     unsigned char* a_lo = smem + L.a_lo;
     float* b_hi = reinterpret_cast<float*>(smem + L.b_hi);
     float* b_lo = reinterpret_cast<float*>(smem + L.b_lo);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);       // TMA -> split
-    uint64_t* ready = full + kTcStages;                                // split -> MMA
-    uint64_t* empty = ready + kTcStages;                               // MMA -> TMA
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);       // TMA -> split          [raw_stages]
+    uint64_t* raw_free = full + kTcMaxRawStages;                       // split -> TMA          [raw_stages]
+    uint64_t* ready = raw_free + kTcMaxRawStages;                      // split -> MMA          [kTcStages]
+    uint64_t* empty = ready + kTcStages;                               // MMA -> split          [kTcStages]
     uint64_t* tmem_full = empty + kTcStages;                           // MMA -> epilogue   [2]
     uint64_t* tmem_empty = tmem_full + 2;                              // epilogue -> MMA   [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&ready[s], 4); tc_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < raw_stages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&raw_free[s], 4); }
+        for (int s = 0; s < kTcStages; ++s) { tc_mbar_init(&ready[s], 4); tc_mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { tc_mbar_init(&tmem_full[b], 1); tc_mbar_init(&tmem_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -172,11 +183,10 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int x0 = (int)(tile * kTcTileCols);
                 for (int ks = 0; ks < nstages_per_tile; ++ks, ++it) {
-                    const int s = it % kTcStages;
-                    tc_mbar_wait(&empty[s], ((it / kTcStages) & 1u) ^ 1u);
+                    const int s = it % raw_stages;
+                    tc_mbar_wait(&raw_free[s], ((it / raw_stages) & 1u) ^ 1u);
                     tc_mbar_expect_tx(&full[s], kTcStageBytes);
-                    for (int b = 0; b < 4; ++b)                        // four [16 x 32] boxes: MN blocks 2 KB apart
-                        tc_tma_box(a_hi + (size_t)s * kTcStageBytes + b * 2048, &tmap, x0 + 32 * b, ks * kTcStageRows, &full[s]);
+                    tc_tma_box(raw + (size_t)s * kTcStageBytes, &tmap, x0, ks * kTcStageRows, &full[s]);
                 }
             }
         }
@@ -197,10 +207,12 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
                 if (lane == 0) {
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
-                        const uint32_t ah = tc_smem_u32(a_hi + (size_t)s * kTcStageBytes + a * 1024);
-                        const uint32_t al = tc_smem_u32(a_lo + (size_t)s * kTcStageBytes + a * 1024);
+                        // K atom a of the stage = k-quads 2a, 2a+1 (2 KB each): LBO = 2 KB between the quads, SBO = 128 B
+                        // between the 8-column core-matrix rows groups
+                        const uint32_t ah = tc_smem_u32(a_hi + (size_t)s * kTcStageBytes + a * 4096);
+                        const uint32_t al = tc_smem_u32(a_lo + (size_t)s * kTcStageBytes + a * 4096);
                         const uint32_t kc = (uint32_t)(ks * 2 + a);
-                        const uint64_t da_hi = tc_desc(ah, 2048, 1024, 2), da_lo = tc_desc(al, 2048, 1024, 2);
+                        const uint64_t da_hi = tc_desc(ah, 2048, 128, 0), da_lo = tc_desc(al, 2048, 128, 0);
                         const uint64_t db_hi = tc_desc(tc_smem_u32(b_hi) + kc * b_chunk, b_lbo, 128, 0);
                         const uint64_t db_lo = tc_desc(tc_smem_u32(b_lo) + kc * b_chunk, b_lbo, 128, 0);
                         tc_mma_tf32(d_addr, da_hi, db_hi, idesc, (ks | a) ? 1u : 0u);
@@ -214,24 +226,31 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
             }
         }
     } else if (warp < 6) {
-        // ===== split warps: q -> (q_hi in place, q_lo) =====
-        const int st = tid - 64;                                       // 0..127
+        // ===== transpose + split warps: raw [16 rows][128 columns] -> K-major core matrices of q_hi and q_lo =====
+        const int x = tid - 64;                                        // the tile column this thread owns, 0..127
+        const uint32_t dst_off = (uint32_t)(x >> 3) * 128u + (uint32_t)(x & 7) * 16u;
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int ks = 0; ks < nstages_per_tile; ++ks, ++it) {
-                const int s = it % kTcStages;
-                tc_mbar_wait(&full[s], (it / kTcStages) & 1u);
-                float4* hi4 = reinterpret_cast<float4*>(a_hi + (size_t)s * kTcStageBytes);
-                float4* lo4 = reinterpret_cast<float4*>(a_lo + (size_t)s * kTcStageBytes);
+                const int rs = it % raw_stages, s = it % kTcStages;
+                tc_mbar_wait(&full[rs], (it / raw_stages) & 1u);       // the raw tile has landed
+                const float* src = reinterpret_cast<const float*>(raw + (size_t)rs * kTcStageBytes) + x;
+                float q[kTcStageRows];
 #pragma unroll
-                for (int k = 0; k < kTcStageBytes / 16 / 128; ++k) {   // 4 x 16-byte chunks per thread
-                    const int c = k * 128 + st;
-                    const float4 q = hi4[c];
+                for (int i = 0; i < kTcStageRows; ++i) q[i] = src[i * kTcTileCols];
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(&raw_free[rs]);          // registers hold it: the producer may refill the slot
+                tc_mbar_wait(&empty[s], ((it / kTcStages) & 1u) ^ 1u); // the MMAs that read this operand stage are done
+                unsigned char* hi = a_hi + (size_t)s * kTcStageBytes + dst_off;
+                unsigned char* lo = a_lo + (size_t)s * kTcStageBytes + dst_off;
+#pragma unroll
+                for (int kq = 0; kq < kTcStageRows / 4; ++kq) {
                     float4 h, l;
-                    h.x = tf32_hi(q.x); h.y = tf32_hi(q.y); h.z = tf32_hi(q.z); h.w = tf32_hi(q.w);
-                    l.x = tf32_hi(q.x - h.x); l.y = tf32_hi(q.y - h.y); l.z = tf32_hi(q.z - h.z); l.w = tf32_hi(q.w - h.w);
-                    hi4[c] = h;
-                    lo4[c] = l;
+                    h.x = tf32_hi(q[4 * kq]); h.y = tf32_hi(q[4 * kq + 1]); h.z = tf32_hi(q[4 * kq + 2]); h.w = tf32_hi(q[4 * kq + 3]);
+                    l.x = tf32_hi(q[4 * kq] - h.x); l.y = tf32_hi(q[4 * kq + 1] - h.y);
+                    l.z = tf32_hi(q[4 * kq + 2] - h.z); l.w = tf32_hi(q[4 * kq + 3] - h.w);
+                    *reinterpret_cast<float4*>(hi + kq * 2048) = h;
+                    *reinterpret_cast<float4*>(lo + kq * 2048) = l;
                 }
                 tc_fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
@@ -298,15 +317,17 @@ int ritz_vectors_tc(const float* Q, int64_t ldq, int m, const float* Y, int ldy,
     if (enc == nullptr) return HLV_OK;
     const int n_cols = nvec <= 16 ? 16 : (nvec + 15) / 16 * 16;
     const int kchunks_pad = 2 * (((m + 7) / 8 + 1) / 2);
-    const size_t smem = ritz_tc_layout(kchunks_pad, n_cols).total + 1024;          // + slack for the 1024-byte alignment
+    int raw_stages = kTcMaxRawStages;                                                // as deep as the 227 KB allow
+    while (raw_stages > 2 && ritz_tc_layout(kchunks_pad, n_cols, raw_stages).total + 1024 > 227 * 1024) --raw_stages;
+    const size_t smem = ritz_tc_layout(kchunks_pad, n_cols, raw_stages).total + 1024;   // + slack for the alignment of the carve-up
     if (smem > 227 * 1024) return HLV_OK;
     CUtensorMap map;
     const cuuint64_t gdim[2] = {(cuuint64_t)(ntiles * kTcTileCols), (cuuint64_t)m};
     const cuuint64_t gstride[1] = {(cuuint64_t)ldq * sizeof(float)};
-    const cuuint32_t box[2] = {32, (cuuint32_t)kTcStageRows};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcTileCols, (cuuint32_t)kTcStageRows};
     const cuuint32_t estride[2] = {1, 1};
     const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Q), gdim, gstride, box, estride,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     HLV_REQUIRE(r == CUDA_SUCCESS, HLV_ERR_ARG, "hlv_ritz_vectors_f32: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     const void* fn = reinterpret_cast<const void*>(ritz_vectors_tc_kernel);
@@ -314,7 +335,7 @@ int ritz_vectors_tc(const float* Q, int64_t ldq, int m, const float* Y, int ldy,
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ritz_vectors_tc)");
     int64_t grid = sm_count();
     if (grid > ntiles) grid = ntiles;
-    ritz_vectors_tc_kernel<<<(int)grid, kTcThreads, smem, stream>>>(map, m, Y, ldy, v0, nvec, n_cols, out, ldo, ntiles);
+    ritz_vectors_tc_kernel<<<(int)grid, kTcThreads, smem, stream>>>(map, m, Y, ldy, v0, nvec, n_cols, out, ldo, ntiles, raw_stages);
     HLV_LAUNCH_CHECK("hlv_ritz_vectors_f32 (tensor-core pass)");
     *n_main_out = ntiles * kTcTileCols;
     return HLV_OK;
