@@ -387,12 +387,21 @@ static size_t slab_budget() {
     return budget;
 }
 
+// Two CTAs per SM is what hides a tile's load behind the other CTA's compute passes, so the tile is the widest one whose
+// WHOLE shared-memory layout (slab + w tile + slice partials + coefficients + barriers) fits twice into the SM's 227 KB
+// (1 KB per CTA is reserved by the system).  Round 1 budgeted the slab alone: bf16 rows at 512-column tiles came to 118 KB,
+// one CTA per SM, and ncu showed the refill bubble (57% of DRAM peak).
+constexpr size_t kFusedTotalPerCta = 112 * 1024;
 template <typename BT>
 static int pick_cpt(int rows) {
     const int max_cpt = sizeof(BT) == 4 ? 4 : 8;          // one 16-byte chunk per thread per row at the widest
     const int rows_pad = (rows + kGroup - 1) / kGroup * kGroup;          // the slab holds whole 8-row boxes
-    for (int cpt = max_cpt; cpt >= 1; cpt >>= 1)
-        if ((size_t)rows_pad * kFusedConsumers * cpt * sizeof(BT) <= slab_budget()) return cpt;
+    const bool two_ctas = slab_budget() == (size_t)kFusedSlabBytes;      // default policy (no HLV_FUSED_SLAB_KB override)
+    for (int cpt = max_cpt; cpt >= 1; cpt >>= 1) {
+        if ((size_t)rows_pad * kFusedConsumers * cpt * sizeof(BT) > slab_budget()) continue;
+        if (two_ctas && cpt > 1 && fused_layout(rows, kFusedConsumers * cpt, (int)sizeof(BT)).total > kFusedTotalPerCta) continue;
+        return cpt;
+    }
     return 0;
 }
 

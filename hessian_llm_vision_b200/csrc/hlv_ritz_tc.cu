@@ -16,15 +16,17 @@
 // Warp roles (320 threads, one CTA per SM, persistent over tiles):
 //   warp 0      TMA producer: one [16 rows x 128 columns] box (8 KB, row-major as in HBM) per stage into a 3-deep ring;
 //               rows >= m arrive as zeros
-//   warps 2-5   transpose + split: the contraction runs over the ROWS of the tile, so the operand has to be K-major =
-//               "basis-row index contiguous".  Thread t owns column x = t of the tile: it reads its 16 values of the stage
-//               (conflict-free scalar loads), and writes q_hi / q_lo as four 16-byte core-matrix rows each (conflict-free
-//               128-bit stores) in the canonical K-major no-swizzle UMMA layout; fence.proxy.async; arrive.  (The hardware's
-//               own transposing path -- an MN-major tf32 descriptor over the TMA-swizzled tile -- returned zeros on this
-//               part in every descriptor variant tried, so the transpose is done in the pass that has to split anyway.)
-//   warp 1      MMA issuer (one elected lane): 3 tcgen05.mma per 8-row K atom, tcgen05.commit frees the stage for the
-//               split warps; after the last atom of a tile a commit hands the accumulator to the epilogue.  Also owns the TMEM
-//               allocation (2 x 128 columns: the accumulator is double-buffered, so tile t+1 is multiplied while tile t drains)
+//   warps 2-5   transpose + split: the contraction runs over the ROWS of the tile, so the A operand must have the basis-row
+//               index as its K dimension.  Thread t owns column x of the tile = TMEM lane x: it reads its 16 values of the
+//               stage from shared memory (conflict-free scalar loads), splits them into q_hi / q_lo and writes both with
+//               one tcgen05.st each into the A-operand ring IN TENSOR MEMORY (lane = x, 16 columns = the stage's rows) --
+//               the transpose is free, and the MMA takes A from TMEM, which halves the shared-memory traffic per tile.
+//               (The hardware's own transposing path -- an MN-major tf32 shared-memory descriptor over the TMA-swizzled
+//               tile -- returned zeros on this part in every descriptor variant tried.)
+//   warp 1      MMA issuer (one elected lane): 3 tcgen05.mma (A from TMEM, B = Y from shared memory) per 8-row K atom,
+//               tcgen05.commit frees the operand stage for the split warps; after the last atom of a tile a commit hands the
+//               accumulator to the epilogue.  Also owns the TMEM allocation (512 columns: two 128-column accumulators, so
+//               tile t+1 is multiplied while tile t drains, + 4 operand stages of 32 columns)
 //   warps 6-9   epilogue: tcgen05.ld 32x32b (lane = column x of the tile), one coalesced 128-byte store per output row
 // Y (hi and lo, zero padded) is staged once per CTA in the same K-major no-swizzle core-matrix layout.
 #include <cuda.h>
@@ -37,14 +39,15 @@ namespace hlv {
 
 constexpr int kTcTileCols = 128;                 // UMMA M
 constexpr int kTcStageRows = 16;                 // two K atoms of 8 rows per pipeline stage
-constexpr int kTcStages = 3;                     // (hi, lo) operand stages between the split warps and the MMA issuer
+constexpr int kTcStages = 4;                     // (hi, lo) operand stages IN TENSOR MEMORY between the split warps and the MMA issuer
 constexpr int kTcMaxRawStages = 12;              // raw tiles between the TMA producer and the split warps: as many as fit
                                                  // (HBM latency x 44 GB/s per SM wants >= 48 KB of loads in flight per SM)
 constexpr int kTcStageBytes = kTcStageRows * kTcTileCols * 4;        // 8 KB (raw) / 8 KB (hi) + 8 KB (lo)
 constexpr int kTcThreads = 320;
 constexpr int kTcMaxN = 112;
 constexpr int kTcMaxM = 128;
-constexpr int kTcTmemCols = 256;                 // two accumulators of up to 128 columns
+constexpr int kTcTmemCols = 512;                 // two accumulators of up to 128 columns + the A-operand ring
+constexpr int kTcTmemA = 256;                    // first column of the A ring: stage s = [hi: 16 columns][lo: 16 columns]
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,7 +89,28 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-// 16 consecutive accumulator columns of this thread's TMEM lane
+// A operand from tensor memory (lane = row of A, consecutive columns = K), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 16 consecutive columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+                   "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]) : "memory");
+}
+// 16 consecutive accumulator columns of this thread's TMEM lane (the caller waits: tcgen05.wait::ld)
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -115,9 +139,8 @@ struct RitzTcSmem {
 __host__ __device__ inline RitzTcSmem ritz_tc_layout(int kchunks_pad, int n_cols, int raw_stages) {
     RitzTcSmem L;
     L.raw = 0;
-    L.a_hi = (size_t)raw_stages * kTcStageBytes;
-    L.a_lo = L.a_hi + (size_t)kTcStages * kTcStageBytes;
-    L.b_hi = L.a_lo + (size_t)kTcStages * kTcStageBytes;
+    L.a_hi = L.a_lo = 0;                                                 // the A operand lives in tensor memory
+    L.b_hi = (size_t)raw_stages * kTcStageBytes;
     const size_t b_bytes = (size_t)kchunks_pad * n_cols * 32;            // per K chunk: [2 halves][n_cols/8][8][4 floats]
     L.b_lo = L.b_hi + b_bytes;
     L.bars = L.b_lo + b_bytes;
@@ -137,8 +160,6 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
     const int kchunks_pad = 2 * nstages_per_tile;
     const RitzTcSmem L = ritz_tc_layout(kchunks_pad, n_cols, raw_stages);
     unsigned char* raw = smem + L.raw;
-    unsigned char* a_hi = smem + L.a_hi;
-    unsigned char* a_lo = smem + L.a_lo;
     float* b_hi = reinterpret_cast<float*>(smem + L.b_hi);
     float* b_lo = reinterpret_cast<float*>(smem + L.b_lo);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);       // TMA -> split          [raw_stages]
@@ -207,17 +228,14 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
                 if (lane == 0) {
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
-                        // K atom a of the stage = k-quads 2a, 2a+1 (2 KB each): LBO = 2 KB between the quads, SBO = 128 B
-                        // between the 8-column core-matrix rows groups
-                        const uint32_t ah = tc_smem_u32(a_hi + (size_t)s * kTcStageBytes + a * 4096);
-                        const uint32_t al = tc_smem_u32(a_lo + (size_t)s * kTcStageBytes + a * 4096);
+                        // K atom a of the stage: 8 columns of the (hi | lo) operand stage in tensor memory
+                        const uint32_t ah = tmem_base + kTcTmemA + (uint32_t)s * 32u + (uint32_t)a * 8u, al = ah + 16u;
                         const uint32_t kc = (uint32_t)(ks * 2 + a);
-                        const uint64_t da_hi = tc_desc(ah, 2048, 128, 0), da_lo = tc_desc(al, 2048, 128, 0);
                         const uint64_t db_hi = tc_desc(tc_smem_u32(b_hi) + kc * b_chunk, b_lbo, 128, 0);
                         const uint64_t db_lo = tc_desc(tc_smem_u32(b_lo) + kc * b_chunk, b_lbo, 128, 0);
-                        tc_mma_tf32(d_addr, da_hi, db_hi, idesc, (ks | a) ? 1u : 0u);
-                        tc_mma_tf32(d_addr, da_lo, db_hi, idesc, 1u);
-                        tc_mma_tf32(d_addr, da_hi, db_lo, idesc, 1u);
+                        tc_mma_tf32_ts(d_addr, ah, db_hi, idesc, (ks | a) ? 1u : 0u);
+                        tc_mma_tf32_ts(d_addr, al, db_hi, idesc, 1u);
+                        tc_mma_tf32_ts(d_addr, ah, db_lo, idesc, 1u);
                     }
                     tc_commit(&empty[s]);                               // stage free once these MMAs have read it
                     if (ks == nstages_per_tile - 1) tc_commit(&tmem_full[acc]);
@@ -226,33 +244,33 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
             }
         }
     } else if (warp < 6) {
-        // ===== transpose + split warps: raw [16 rows][128 columns] -> K-major core matrices of q_hi and q_lo =====
-        const int x = tid - 64;                                        // the tile column this thread owns, 0..127
-        const uint32_t dst_off = (uint32_t)(x >> 3) * 128u + (uint32_t)(x & 7) * 16u;
+        // ===== transpose + split warps: raw [16 rows][128 columns] -> q_hi, q_lo rows of the A operand in TENSOR MEMORY =====
+        // Thread = column x of the tile = TMEM lane (a warp may touch the lane quarter (warp % 4) only): it reads its 16 values
+        // of the stage from shared memory (conflict-free), splits them and stores both halves with one tcgen05.st each --
+        // the transpose costs nothing, and the MMA reads A from tensor memory instead of shared memory.
+        const int x = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTcTmemA;
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int ks = 0; ks < nstages_per_tile; ++ks, ++it) {
                 const int rs = it % raw_stages, s = it % kTcStages;
                 tc_mbar_wait(&full[rs], (it / raw_stages) & 1u);       // the raw tile has landed
                 const float* src = reinterpret_cast<const float*>(raw + (size_t)rs * kTcStageBytes) + x;
-                float q[kTcStageRows];
+                float h[kTcStageRows], l[kTcStageRows];
 #pragma unroll
-                for (int i = 0; i < kTcStageRows; ++i) q[i] = src[i * kTcTileCols];
+                for (int i = 0; i < kTcStageRows; ++i) {
+                    const float q = src[i * kTcTileCols];
+                    h[i] = tf32_hi(q);
+                    l[i] = tf32_hi(q - h[i]);
+                }
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(&raw_free[rs]);          // registers hold it: the producer may refill the slot
                 tc_mbar_wait(&empty[s], ((it / kTcStages) & 1u) ^ 1u); // the MMAs that read this operand stage are done
-                unsigned char* hi = a_hi + (size_t)s * kTcStageBytes + dst_off;
-                unsigned char* lo = a_lo + (size_t)s * kTcStageBytes + dst_off;
-#pragma unroll
-                for (int kq = 0; kq < kTcStageRows / 4; ++kq) {
-                    float4 h, l;
-                    h.x = tf32_hi(q[4 * kq]); h.y = tf32_hi(q[4 * kq + 1]); h.z = tf32_hi(q[4 * kq + 2]); h.w = tf32_hi(q[4 * kq + 3]);
-                    l.x = tf32_hi(q[4 * kq] - h.x); l.y = tf32_hi(q[4 * kq + 1] - h.y);
-                    l.z = tf32_hi(q[4 * kq + 2] - h.z); l.w = tf32_hi(q[4 * kq + 3] - h.w);
-                    *reinterpret_cast<float4*>(hi + kq * 2048) = h;
-                    *reinterpret_cast<float4*>(lo + kq * 2048) = l;
-                }
-                tc_fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
+                tc_fence_after();
+                tc_st16(lane_addr + (uint32_t)s * 32u, h);
+                tc_st16(lane_addr + (uint32_t)s * 32u + 16u, l);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(&ready[s]);
             }
@@ -267,12 +285,32 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
             tc_fence_after();
             const int64_t x = tile * kTcTileCols + q * 32 + lane;
             const uint32_t taddr = tmem_base + acc * 128u + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < n_cols; c0 += 16) {
-                uint32_t v[16];
-                tc_ld16(taddr + c0, v);
+            float* dst = out + (int64_t)v0 * ldo + x;
+            // 32 columns per round: both loads are issued before the single wait, the stores of full chunks carry no predicate
+            for (int c0 = 0; c0 < n_cols; c0 += 32) {
+                uint32_t va[16], vb[16];
+                const bool second = c0 + 16 < n_cols;
+                tc_ld16_nowait(taddr + c0, va);
+                if (second) tc_ld16_nowait(taddr + c0 + 16, vb);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 16 <= nvec) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < nvec) out[(int64_t)(v0 + c0 + j) * ldo + x] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 16; ++j) dst[(int64_t)(c0 + j) * ldo] = __uint_as_float(va[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < nvec) dst[(int64_t)(c0 + j) * ldo] = __uint_as_float(va[j]);
+                }
+                if (second) {
+                    if (c0 + 32 <= nvec) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) dst[(int64_t)(c0 + 16 + j) * ldo] = __uint_as_float(vb[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + 16 + j < nvec) dst[(int64_t)(c0 + 16 + j) * ldo] = __uint_as_float(vb[j]);
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
