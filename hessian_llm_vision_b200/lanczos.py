@@ -186,7 +186,7 @@ class LanczosEngine:
                  basis_dtype: torch.dtype = torch.float32, keep_basis: Optional[bool] = None,
                  breakdown_tol: Optional[float] = None, comm: Optional[Comm] = None,
                  profile: bool = False, column_vectors: bool = False, cgs_passes: int = 2, fused_cgs: bool = True,
-                 reorth_tol: Optional[float] = None, exchange: str = "auto", peer=None):
+                 reorth_tol: Optional[float] = None, exchange: str = "auto", peer=None, peer_allgather: Optional[bool] = None):
         if reorth not in (None, "full"):
             raise ValueError("reorth must be None or 'full'")
         if basis_dtype not in (torch.float32, torch.bfloat16):
@@ -256,7 +256,7 @@ class LanczosEngine:
         # kernels over NVLink peer memory (csrc/hlv_peer.cuh)
         self.peer = None
         self.multicast = False
-        self.peer_allgather = True
+        self.peer_allgather = peer_allgather
         self._v_pending = False
         self.exchange_mode = "none" if G == 1 else "nccl"
         if exchange not in ("auto", "peer", "nccl"):
@@ -303,12 +303,16 @@ class LanczosEngine:
         self.hv_full = peer.hv_full[: self.n_pad]
         self.v_full = peer.v_full[: self.n_pad]
         import os
-        # tuning knobs (measured defaults, profiles/README.md): HLV_MULTICAST=0/1 forces the NVSwitch multicast paths off / on
-        # (default: on from 4 ranks -- with one peer there is nothing to replicate or reduce in the switch);
-        # HLV_PEER_ALLGATHER=nccl keeps the collective for v_{j+1} and fuses only the reduce-scatter and the scalars
+        # Measured defaults (8 x B200, profiles/r02_bench_n8_k20_exchange_*.json; knobs for A/B runs):
+        #  * the reduce-scatter + alpha kernel and the in-kernel coefficient exchange are always used;
+        #  * v_{j+1} is all-gathered by NCCL: its NVLS all-gather (0.73 ms for 8 x 62 MB) beats this library's peer stores
+        #    from the normalise kernel (1.5 ms, unicast or multimem.st alike) -- HLV_PEER_ALLGATHER=peer selects the stores;
+        #  * HLV_MULTICAST=0/1 forces the NVSwitch multicast paths off / on (default: on from 4 ranks -- with one peer there
+        #    is nothing to replicate or reduce in the switch).
         mc = os.environ.get("HLV_MULTICAST", "auto")
         self.multicast = bool(peer.hv_multicast and peer.v_multicast) and (mc == "1" or (mc == "auto" and peer.world >= 4))
-        self.peer_allgather = os.environ.get("HLV_PEER_ALLGATHER", "peer") != "nccl"
+        if self.peer_allgather is None:
+            self.peer_allgather = os.environ.get("HLV_PEER_ALLGATHER", "nccl") == "peer"
         self.exchange_mode = ("peer+multicast" if self.multicast else "peer") + ("" if self.peer_allgather else "+nccl_allgather")
 
     # -- vectors ---------------------------------------------------------------

@@ -91,7 +91,7 @@ def _engines(hlv, world, n, m, cuda_dev, reorth, basis_dtype, parts):
     for r in range(world):
         part = parts[r]
         engs.append(hlv.LanczosEngine(lambda v, part=part: part(v), n, m, cuda_dev, reorth=reorth, basis_dtype=basis_dtype,
-                                      comm=emu.EmulatedComm(world, r), exchange="peer", peer=ctxs[r]))
+                                      comm=emu.EmulatedComm(world, r), exchange="peer", peer=ctxs[r], peer_allgather=True))
     return engs, ctxs
 
 
@@ -112,7 +112,7 @@ def test_sharded_engine_over_emulated_peers(cuda_dev, libhlv, world, n, m, reort
     v0 /= v0.norm()
     engs, ctxs = _engines(hlv, world, n, m, cuda_dev, reorth, basis_dtype, parts)
     for e in engs:
-        assert e.exchange_mode == "peer"
+        assert e.exchange_mode == "peer"          # every exchange step inside the kernels (no collective exists in the emulation)
         e.start(v0)
     for j in range(m):
         emu.lockstep(engs, j)
@@ -155,10 +155,11 @@ per = 8 // world                                     # H = mean of 8 diagonal op
 mine = (d[rank * per:(rank + 1) * per].sum(0) / 8).cuda()
 out = {}
 os.environ["HLV_MULTICAST"] = os.environ.get("HLV_TEST_MULTICAST", "1")
-for name, kw in (("nccl", dict(exchange="nccl")), ("peer", dict(exchange="peer")),
+for name, kw in (("nccl", dict(exchange="nccl")), ("peer", dict(exchange="peer")), ("peer_stores", dict(exchange="peer", env="peer")),
                  ("peer_bf16", dict(exchange="peer", basis_dtype=torch.bfloat16)), ("nccl_bf16", dict(exchange="nccl", basis_dtype=torch.bfloat16)),
                  ("peer_noreorth", dict(exchange="peer", reorth=None)), ("nccl_noreorth", dict(exchange="nccl", reorth=None))):
     kw.setdefault("reorth", "full")
+    os.environ["HLV_PEER_ALLGATHER"] = kw.pop("env", "nccl")      # default: NCCL all-gather of v; "peer": stores from the normalise kernel
     try:
         eng = hlv.LanczosEngine(lambda q: mine * q, n, m, torch.device("cuda", rank), comm=hlv.Comm(), **kw)
         eng.start(v0)
@@ -210,9 +211,10 @@ def test_rank_count_invariance_nccl_and_peer_exchange(cuda_dev, libhlv, tmp_path
                          ("_noreorth", dict(reorth=None), 2e-3)):
         one = hlv.lanczos(lambda q: dm * q, m, v0, **kw)
         scale = float(one.T.abs().max())
-        for mode in ("nccl", "peer"):
+        for mode in ("nccl", "peer") + (("peer_stores",) if sfx == "" else ()):
             g = got[mode + sfx]
             assert "error" not in g, (mode + sfx, g)
-            assert g["mode"].startswith(mode), (mode + sfx, g["mode"])
+            assert g["mode"].startswith(mode.split("_")[0]), (mode + sfx, g["mode"])
+            assert ("nccl_allgather" in g["mode"]) == (mode == "peer"), g["mode"]
             assert float((g["T"] - one.T).abs().max()) / scale < tol, (mode + sfx, world)
         assert float((got["peer" + sfx]["T"] - got["nccl" + sfx]["T"]).abs().max()) / scale < (1e-6 if sfx == "" else tol)
