@@ -365,6 +365,8 @@ def run_ours(args, rank, world, local_rank):
             clocks.start()
         launches0 = kernels.launch_count
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if os.environ.get("HLV_PROFILE_RANGE") == "1" and not e2e:     # `ncu --profile-from-start off`: only the timed steps
+            torch.cuda.profiler.start()
         ev0.record()
         sink = 0.0
         for j in sched:
@@ -375,6 +377,8 @@ def run_ours(args, rank, world, local_rank):
             op.drain()                                    # a prefetched half-application is work of this region: wait for it
         ev1.record()
         torch.cuda.synchronize(); comm.barrier()
+        if os.environ.get("HLV_PROFILE_RANGE") == "1" and not e2e:
+            torch.cuda.profiler.stop()
         ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
