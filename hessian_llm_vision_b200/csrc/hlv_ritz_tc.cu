@@ -136,11 +136,12 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 struct RitzTcSmem {
     size_t raw, a_hi, a_lo, b_hi, b_lo, bars, tmem_slot, total;
 };
-__host__ __device__ inline RitzTcSmem ritz_tc_layout(int kchunks_pad, int n_cols, int raw_stages) {
+__host__ __device__ inline RitzTcSmem ritz_tc_layout(int kchunks_pad, int n_cols, int raw_stages, bool a_tmem) {
     RitzTcSmem L;
     L.raw = 0;
-    L.a_hi = L.a_lo = 0;                                                 // the A operand lives in tensor memory
-    L.b_hi = (size_t)raw_stages * kTcStageBytes;
+    L.a_hi = (size_t)raw_stages * kTcStageBytes;                         // A operand stages in shared memory (SS form) ...
+    L.a_lo = L.a_hi + (a_tmem ? 0 : (size_t)kTcStages * kTcStageBytes);  // ... or none: the operand lives in tensor memory
+    L.b_hi = L.a_lo + (a_tmem ? 0 : (size_t)kTcStages * kTcStageBytes);
     const size_t b_bytes = (size_t)kchunks_pad * n_cols * 32;            // per K chunk: [2 halves][n_cols/8][8][4 floats]
     L.b_lo = L.b_hi + b_bytes;
     L.bars = L.b_lo + b_bytes;
@@ -149,6 +150,7 @@ __host__ __device__ inline RitzTcSmem ritz_tc_layout(int kchunks_pad, int n_cols
     return L;
 }
 
+template <bool A_TMEM>
 __global__ void __launch_bounds__(kTcThreads, 1)
 ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const float* __restrict__ Y, int ldy, int v0, int nvec,
                        int n_cols, float* __restrict__ out, int64_t ldo, int64_t ntiles, int raw_stages) {
@@ -158,8 +160,10 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
     const int kchunks = (m + 7) / 8;
     const int nstages_per_tile = (kchunks + 1) / 2;
     const int kchunks_pad = 2 * nstages_per_tile;
-    const RitzTcSmem L = ritz_tc_layout(kchunks_pad, n_cols, raw_stages);
+    const RitzTcSmem L = ritz_tc_layout(kchunks_pad, n_cols, raw_stages, A_TMEM);
     unsigned char* raw = smem + L.raw;
+    unsigned char* a_hi = smem + L.a_hi;
+    unsigned char* a_lo = smem + L.a_lo;
     float* b_hi = reinterpret_cast<float*>(smem + L.b_hi);
     float* b_lo = reinterpret_cast<float*>(smem + L.b_lo);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);       // TMA -> split          [raw_stages]
@@ -228,14 +232,24 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
                 if (lane == 0) {
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
-                        // K atom a of the stage: 8 columns of the (hi | lo) operand stage in tensor memory
-                        const uint32_t ah = tmem_base + kTcTmemA + (uint32_t)s * 32u + (uint32_t)a * 8u, al = ah + 16u;
                         const uint32_t kc = (uint32_t)(ks * 2 + a);
                         const uint64_t db_hi = tc_desc(tc_smem_u32(b_hi) + kc * b_chunk, b_lbo, 128, 0);
                         const uint64_t db_lo = tc_desc(tc_smem_u32(b_lo) + kc * b_chunk, b_lbo, 128, 0);
-                        tc_mma_tf32_ts(d_addr, ah, db_hi, idesc, (ks | a) ? 1u : 0u);
-                        tc_mma_tf32_ts(d_addr, al, db_hi, idesc, 1u);
-                        tc_mma_tf32_ts(d_addr, ah, db_lo, idesc, 1u);
+                        if constexpr (A_TMEM) {
+                            // K atom a of the stage: 8 columns of the (hi | lo) operand stage in tensor memory
+                            const uint32_t ah = tmem_base + kTcTmemA + (uint32_t)s * 32u + (uint32_t)a * 8u, al = ah + 16u;
+                            tc_mma_tf32_ts(d_addr, ah, db_hi, idesc, (ks | a) ? 1u : 0u);
+                            tc_mma_tf32_ts(d_addr, al, db_hi, idesc, 1u);
+                            tc_mma_tf32_ts(d_addr, ah, db_lo, idesc, 1u);
+                        } else {
+                            // K atom a = k-quads 2a, 2a+1 of the stage (2 KB each): LBO = 2 KB between the quads, SBO = 128 B
+                            // between the 8-column groups of core-matrix rows
+                            const uint64_t da_hi = tc_desc(tc_smem_u32(a_hi + (size_t)s * kTcStageBytes + a * 4096), 2048, 128, 0);
+                            const uint64_t da_lo = tc_desc(tc_smem_u32(a_lo + (size_t)s * kTcStageBytes + a * 4096), 2048, 128, 0);
+                            tc_mma_tf32(d_addr, da_hi, db_hi, idesc, (ks | a) ? 1u : 0u);
+                            tc_mma_tf32(d_addr, da_lo, db_hi, idesc, 1u);
+                            tc_mma_tf32(d_addr, da_hi, db_lo, idesc, 1u);
+                        }
                     }
                     tc_commit(&empty[s]);                               // stage free once these MMAs have read it
                     if (ks == nstages_per_tile - 1) tc_commit(&tmem_full[acc]);
@@ -266,11 +280,23 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(&raw_free[rs]);          // registers hold it: the producer may refill the slot
                 tc_mbar_wait(&empty[s], ((it / kTcStages) & 1u) ^ 1u); // the MMAs that read this operand stage are done
-                tc_fence_after();
-                tc_st16(lane_addr + (uint32_t)s * 32u, h);
-                tc_st16(lane_addr + (uint32_t)s * 32u + 16u, l);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
+                if constexpr (A_TMEM) {
+                    tc_fence_after();
+                    tc_st16(lane_addr + (uint32_t)s * 32u, h);
+                    tc_st16(lane_addr + (uint32_t)s * 32u + 16u, l);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                } else {
+                    // K-major no-swizzle core matrices: (x, i) at (i / 4) * 2 KB + (x / 8) * 128 + (x % 8) * 16 + (i % 4) * 4
+                    unsigned char* hi = a_hi + (size_t)s * kTcStageBytes + (x >> 3) * 128 + (x & 7) * 16;
+                    unsigned char* lo = a_lo + (size_t)s * kTcStageBytes + (x >> 3) * 128 + (x & 7) * 16;
+#pragma unroll
+                    for (int kq = 0; kq < kTcStageRows / 4; ++kq) {
+                        *reinterpret_cast<float4*>(hi + kq * 2048) = make_float4(h[4 * kq], h[4 * kq + 1], h[4 * kq + 2], h[4 * kq + 3]);
+                        *reinterpret_cast<float4*>(lo + kq * 2048) = make_float4(l[4 * kq], l[4 * kq + 1], l[4 * kq + 2], l[4 * kq + 3]);
+                    }
+                    tc_fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core
+                }
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(&ready[s]);
             }
@@ -286,35 +312,27 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
             const int64_t x = tile * kTcTileCols + q * 32 + lane;
             const uint32_t taddr = tmem_base + acc * 128u + ((uint32_t)(q * 32) << 16);
             float* dst = out + (int64_t)v0 * ldo + x;
-            // 32 columns per round: both loads are issued before the single wait, the stores of full chunks carry no predicate
-            for (int c0 = 0; c0 < n_cols; c0 += 32) {
-                uint32_t va[16], vb[16];
-                const bool second = c0 + 16 < n_cols;
-                tc_ld16_nowait(taddr + c0, va);
-                if (second) tc_ld16_nowait(taddr + c0 + 16, vb);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 16 <= nvec) {
+            // every load of the tile is issued before ONE wait (tcgen05.ld shares the tensor core's in-order queue with the MMAs of
+            // the next tile: a wait per chunk would queue behind them again and again); stores of full chunks carry no predicate
+            uint32_t v[kTcMaxN / 16][16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dst[(int64_t)(c0 + j) * ldo] = __uint_as_float(va[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < nvec) dst[(int64_t)(c0 + j) * ldo] = __uint_as_float(va[j]);
-                }
-                if (second) {
-                    if (c0 + 32 <= nvec) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) dst[(int64_t)(c0 + 16 + j) * ldo] = __uint_as_float(vb[j]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + 16 + j < nvec) dst[(int64_t)(c0 + 16 + j) * ldo] = __uint_as_float(vb[j]);
-                    }
-                }
-            }
+            for (int k = 0; k < kTcMaxN / 16; ++k)
+                if (k * 16 < n_cols) tc_ld16_nowait(taddr + k * 16, v[k]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc_mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) tc_mbar_arrive(&tmem_empty[acc]);          // the accumulator is in registers: the MMA warp may reuse it
+#pragma unroll
+            for (int k = 0; k < kTcMaxN / 16; ++k) {
+                if (k * 16 + 16 <= nvec) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dst[(int64_t)(k * 16 + j) * ldo] = __uint_as_float(v[k][j]);
+                } else if (k * 16 < nvec) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (k * 16 + j < nvec) dst[(int64_t)(k * 16 + j) * ldo] = __uint_as_float(v[k][j]);
+                }
+            }
         }
     }
     // ===== teardown =====
@@ -355,9 +373,12 @@ int ritz_vectors_tc(const float* Q, int64_t ldq, int m, const float* Y, int ldy,
     if (enc == nullptr) return HLV_OK;
     const int n_cols = nvec <= 16 ? 16 : (nvec + 15) / 16 * 16;
     const int kchunks_pad = 2 * (((m + 7) / 8 + 1) / 2);
+    // HLV_RITZ_A=smem keeps the split operand in shared memory (tcgen05.mma SS form) instead of tensor memory (TS form, default);
+    // both are validated by the tests, measured within 3% of each other (24.0 / 24.6 ms for all 100 vectors at GPT-2 size)
+    static const bool a_tmem = [] { const char* e = getenv("HLV_RITZ_A"); return !(e && e[0] == 's'); }();
     int raw_stages = kTcMaxRawStages;                                                // as deep as the 227 KB allow
-    while (raw_stages > 2 && ritz_tc_layout(kchunks_pad, n_cols, raw_stages).total + 1024 > 227 * 1024) --raw_stages;
-    const size_t smem = ritz_tc_layout(kchunks_pad, n_cols, raw_stages).total + 1024;   // + slack for the alignment of the carve-up
+    while (raw_stages > 2 && ritz_tc_layout(kchunks_pad, n_cols, raw_stages, a_tmem).total + 1024 > 227 * 1024) --raw_stages;
+    const size_t smem = ritz_tc_layout(kchunks_pad, n_cols, raw_stages, a_tmem).total + 1024;   // + slack for the alignment of the carve-up
     if (smem > 227 * 1024) return HLV_OK;
     CUtensorMap map;
     const cuuint64_t gdim[2] = {(cuuint64_t)(ntiles * kTcTileCols), (cuuint64_t)m};
@@ -368,12 +389,18 @@ int ritz_vectors_tc(const float* Q, int64_t ldq, int m, const float* Y, int ldy,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     HLV_REQUIRE(r == CUDA_SUCCESS, HLV_ERR_ARG, "hlv_ritz_vectors_f32: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-    const void* fn = reinterpret_cast<const void*>(ritz_vectors_tc_kernel);
-    cudaError_t e = ensure_dynamic_smem(fn, smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ritz_vectors_tc)");
     int64_t grid = sm_count();
     if (grid > ntiles) grid = ntiles;
-    ritz_vectors_tc_kernel<<<(int)grid, kTcThreads, smem, stream>>>(map, m, Y, ldy, v0, nvec, n_cols, out, ldo, ntiles, raw_stages);
+    cudaError_t e;
+    if (a_tmem) {
+        if ((e = ensure_dynamic_smem(reinterpret_cast<const void*>(ritz_vectors_tc_kernel<true>), smem)) != cudaSuccess)
+            return cuda_fail(e, "cudaFuncSetAttribute(ritz_vectors_tc)");
+        ritz_vectors_tc_kernel<true><<<(int)grid, kTcThreads, smem, stream>>>(map, m, Y, ldy, v0, nvec, n_cols, out, ldo, ntiles, raw_stages);
+    } else {
+        if ((e = ensure_dynamic_smem(reinterpret_cast<const void*>(ritz_vectors_tc_kernel<false>), smem)) != cudaSuccess)
+            return cuda_fail(e, "cudaFuncSetAttribute(ritz_vectors_tc)");
+        ritz_vectors_tc_kernel<false><<<(int)grid, kTcThreads, smem, stream>>>(map, m, Y, ldy, v0, nvec, n_cols, out, ldo, ntiles, raw_stages);
+    }
     HLV_LAUNCH_CHECK("hlv_ritz_vectors_f32 (tensor-core pass)");
     *n_main_out = ntiles * kTcTileCols;
     return HLV_OK;
