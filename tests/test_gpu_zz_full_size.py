@@ -118,3 +118,72 @@ def test_config2_full_size_parity(gpt2, cuda_dev):
     assert err["ritz_top10_rel_vs_f64"] < 1e-4, err                # top-k Ritz values within 1e-4 relative
     assert err["ritz_all_abs_over_scale_vs_f64"] < 1e-5, err
     assert orth < 5e-6, err                                        # the stored rows are orthonormal at fp32 working precision
+
+
+def _oracle_pair(hvp32, v0, m, reorth):
+    """The oracle recurrence in float64 and in float32 (torch CUDA ops) over the same fp32 operator: (f64, f32, scale)."""
+    out = {}
+    for name, dtype in (("f64", torch.float64), ("f32", torch.float32)):
+        ref = oracle.lanczos_cgs2(lambda v: hvp32(v.float()).to(dtype), v0.to(dtype), m, reorth=reorth, dtype=dtype)
+        out[name] = (ref["alphas"].double().cpu(), ref["betas"].double().cpu(), torch.linalg.eigvalsh(ref["T"].double().cpu()),
+                     float(ref["T"].abs().max()))
+        del ref
+        torch.cuda.empty_cache()
+    return out["f64"], out["f32"], out["f64"][3]
+
+
+def test_config1_full_size_dataset_hvp_no_reorth(gpt2, cuda_dev):
+    """BASELINE config 1 at FULL size: GPT-2 124M, 25 iterations, NO reorthogonalisation, 20 sequences (= int(1e-4 * 205,328)
+    documents) streamed as micro-batches 8 + 8 + 4 with B_i/N weights (gpt2_savehessian.py:143-163, lanczostrain_hand.py:171-203)
+    against the oracle over the reference's dataset HVP.  Without reorthogonalisation alpha/beta are rounding-sensitive once the
+    first Ritz value has converged, so the bar is per iteration: 1e-5 of max|T| plus the distance between the oracle's own
+    float32 and float64 evaluations at that iteration."""
+    import hessian_llm_vision_b200 as hlv
+    model, _, v0 = gpt2
+    g = torch.Generator().manual_seed(4321)
+    ids = torch.randint(0, 50257, (20, 512), generator=g).to(cuda_dev)
+    batches = [ids[0:8], ids[8:16], ids[16:20]]
+    m = 25
+    op = hlv.HessianVectorProduct(model, batches)
+    assert op.weights == [8 / 20, 8 / 20, 4 / 20]
+    res = hlv.lanczos(op, m, v0, reorth=None)
+    a, b, ev = res.alphas.double().cpu(), res.betas.double().cpu(), res.eigvals.double().cpu()
+    sum_gamma = float(res.gammas.sum())
+    op.clear_cache()
+    del op, res
+    torch.cuda.empty_cache()
+    f64, f32, scale = _oracle_pair(lambda v: oracle.hess_vec_dataset(v, batches, model), v0, m, None)
+    floor_a, floor_b = (f64[0] - f32[0]).abs() / scale, (f64[1] - f32[1]).abs() / scale
+    err_a, err_b = (a - f64[0]).abs() / scale, (b - f64[1]).abs() / scale
+    rec = {"alpha_err_max": float(err_a.max()), "beta_err_max": float(err_b.max()), "floor_alpha_max": float(floor_a.max()),
+           "floor_beta_max": float(floor_b.max()), "ritz_max_rel": float(abs(ev[-1] - f64[2][-1]) / abs(f64[2][-1])), "T_abs_max": scale}
+    _record("r02_config1_full_size_parity_test.json", rec)
+    print(json.dumps(rec))
+    assert bool((err_a <= 1e-5 + floor_a).all()), rec
+    assert bool((err_b <= 1e-5 + floor_b).all()), rec
+    assert rec["ritz_max_rel"] < 1e-4, rec                          # the converged extreme Ritz value
+    assert abs(sum_gamma - 1.0) < 1e-5
+
+
+def test_config3_full_size_per_block_spectra(gpt2, cuda_dev):
+    """BASELINE config 3 at FULL size for the first and the last transformer block (P_block = 7,087,872 each): one Lanczos run
+    per block, operator restricted to the block's parameters (ipynbs/visual-eigen.ipynb cells 10-12), full reorthogonalisation."""
+    import hessian_llm_vision_b200 as hlv
+    model, ids, _ = gpt2
+    m = 20
+    blocks = [model.transformer.h[0], model.transformer.h[11]]
+    ev, gm = hlv.per_block_spectra(model, [ids], m, blocks=blocks, seed=10)
+    out = {}
+    for i, blk in enumerate(blocks):
+        params = list(blk.parameters())
+        nb = sum(p.numel() for p in params)
+        assert nb == 7_087_872
+        v0 = hlv.probe_vector(nb, 10 + i, cuda_dev)
+        f64, f32, scale = _oracle_pair(lambda v: oracle.hess_vec_subset(v, [ids], model, params), v0, m, "full")
+        floor = float((f64[2] - f32[2]).abs().max()) / scale
+        err = float((ev[i].double() - f64[2]).abs().max()) / scale
+        out[f"block{0 if i == 0 else 11}"] = {"ritz_err_over_scale": err, "floor": floor, "ritz_max": float(f64[2][-1]), "sum_gammas": float(gm[i].sum())}
+        assert err < 1e-5 + floor, out
+        assert abs(float(gm[i].sum()) - 1.0) < 1e-5
+    _record("r02_config3_full_size_parity_test.json", out)
+    print(json.dumps(out))
