@@ -458,6 +458,8 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:  # noqa: BLE001
             extras["error"] = repr(e)[:300]
 
+    if eng.peer is not None and eng.peer.error():
+        raise RuntimeError(f"peer exchange: a wait on channel {eng.peer.error() - 1} ran into its time limit; the numbers are invalid")
     if rank != 0:
         return
     # ---- roofline of the dominant libhlv kernel, from CUDA events inside the timed region ----

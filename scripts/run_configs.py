@@ -5,7 +5,7 @@ parity tests use at small size (orthogonality of the stored rows, sum(gammas) = 
   python scripts/run_configs.py --config 1            # GPT-2, m=25, no reorth, 20 sequences streamed as micro-batches
   python scripts/run_configs.py --config 3 [--iters 20]   # one Lanczos run per transformer block (12 runs, P=7,087,872)
   torchrun --nproc-per-node N scripts/run_configs.py --config 4   # Pythia-1.4B shapes, m=50, bf16 basis sharded along P
-  python scripts/run_configs.py --config 5 [--probes 2]   # SLQ: ResNet-50/10-class 16 probes x 80 + GPT-2 probes x 80
+  [torchrun --nproc-per-node N] python scripts/run_configs.py --config 5 [--probes 16]   # SLQ: ResNet-50/10-class 16 probes x 80 + GPT-2 probes x 80; probes dealt over the ranks
 
 Reference call sites: gpt2_hessian_cpu.py:207-216 / gpt2_savehessian.py:143-163 (1), ipynbs/visual-eigen.ipynb
 cells 10-12 (3), diego_pythia.py:95-192 (4), d.sh:4-11 + train_savespec.py:61-91 (5)."""
@@ -114,17 +114,19 @@ def config4(args, dev, comm):
             "note": "bf16 storage of the rows: orthogonality ~1e-3 (one bf16 ulp), by design"}
 
 
-def config5(args, dev):
+def config5(args, dev, comm):
     import torch.nn as nn
     import torchvision
-    out = {"config": "5: stochastic Lanczos quadrature, 80 iterations per probe"}
+    rep = comm if comm.world > 1 else None          # probes dealt round-robin over the ranks, replicas only (d.sh:4-11 runs them one by one)
+    out = {"config": "5: stochastic Lanczos quadrature, 80 iterations per probe", "ranks": comm.world,
+           "probe_split": "round-robin over ranks, no data-path collective; (eigvals, gammas) exchanged once at the end"}
     torch.manual_seed(0)
     net = torchvision.models.resnet50(num_classes=10).to(dev)
     g = torch.Generator().manual_seed(5)
     x, y = torch.randn(128, 3, 32, 32, generator=g).to(dev), torch.randint(0, 10, (128,), generator=g).to(dev)
     op = hlv.HessianVectorProduct(net, [(x, y)], loss_fn=hlv.criterion_loss(nn.CrossEntropyLoss()), bn_train_mode=True)
     seeds = list(range(16))
-    r, t_dev, _ = timed_run(lambda: hlv.slq(op, op.n, 80, seeds, dev))
+    r, t_dev, _ = timed_run(lambda: hlv.slq(op, op.n, 80, seeds, dev, replicas=rep))
     grid, dens = r.density(num_points=512)
     out["resnet50"] = {"P": op.n, "probes": len(seeds), "iters": 80, "seconds": t_dev, "iterations_per_s": len(seeds) * 80 / t_dev,
                        "sum_gammas_eigeninfo": float(r.eigeninfo()["gammas"].sum()), "density_integral": float(((dens[1:] + dens[:-1]) * 0.5 * (grid[1:] - grid[:-1])).sum()),
@@ -135,7 +137,7 @@ def config5(args, dev):
     batches = [b.to(dev) for b in tokens(cfg.vocab_size, 8, 512, 8)]
     op2 = hlv.HessianVectorProduct(model, batches).capture()
     seeds2 = list(range(args.probes))
-    r2, t_dev2, _ = timed_run(lambda: hlv.slq(op2, op2.n, 80, seeds2, dev))
+    r2, t_dev2, _ = timed_run(lambda: hlv.slq(op2, op2.n, 80, seeds2, dev, replicas=rep))
     out["gpt2"] = {"P": op2.n, "probes": len(seeds2), "of": 16, "iters": 80, "seconds": t_dev2, "iterations_per_s": len(seeds2) * 80 / t_dev2,
                    "sum_gammas_eigeninfo": float(r2.eigeninfo()["gammas"].sum()),
                    "ritz_max_per_probe": [round(float(e[-1]), 4) for e in r2.eigvals]}
@@ -166,7 +168,7 @@ def main():
         elif args.config == 4:
             out = config4(args, dev, comm)
         else:
-            out = config5(args, dev)
+            out = config5(args, dev, comm)
         if comm.rank == 0:
             print(json.dumps(out), flush=True)
     finally:
