@@ -178,6 +178,27 @@ def test_engine_never_adopts_the_operators_buffer(cpu_double):
     assert float((res.T - ref["T"]).abs().max()) / float(ref["T"].abs().max()) < 2e-5
 
 
+def test_exchange_argument_handling(cpu_double):
+    """exchange='peer' needs CUDA devices and the exchange-aware kernels: on the CPU test double it must refuse loudly,
+    'auto' must fall back to the collectives and say why, anything else is an argument error."""
+    import hessian_llm_vision_b200 as hlv
+
+    class TwoRanks:                                     # world/rank only: no process group is touched at construction
+        world, rank, backend, group = 2, 0, "gloo", None
+
+        def barrier(self):
+            pass
+    M, v0 = _sym(2, 32)
+    with pytest.raises(RuntimeError, match="exchange='peer' is not available"):
+        hlv.LanczosEngine(lambda v: M @ v, 32, 4, "cpu", reorth="full", comm=TwoRanks(), exchange="peer")
+    eng = hlv.LanczosEngine(lambda v: M @ v, 32, 4, "cpu", reorth="full", comm=TwoRanks(), exchange="auto")
+    assert eng.peer is None and eng.exchange_mode.startswith("nccl (peer exchange unavailable")
+    assert hlv.LanczosEngine(lambda v: M @ v, 32, 4, "cpu", reorth="full", comm=TwoRanks(), exchange="nccl").exchange_mode == "nccl"
+    assert hlv.LanczosEngine(lambda v: M @ v, 32, 4, "cpu", reorth="full").exchange_mode == "none"
+    with pytest.raises(ValueError, match="exchange must be"):
+        hlv.LanczosEngine(lambda v: M @ v, 32, 4, "cpu", exchange="mpi")
+
+
 def test_engine_breakdown_truncates(cpu_double):
     import hessian_llm_vision_b200 as hlv
     torch.manual_seed(1)
