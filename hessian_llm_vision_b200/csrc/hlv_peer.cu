@@ -1,5 +1,7 @@
 // libhlv.so -- the exchange steps of the sharded recurrence over NVLink peer memory (see hlv_peer.cuh):
 // exchange-area management, flag-only signal / wait, and the reduce-scatter + alpha kernel.
+#include <stdlib.h>
+
 #include "hlv_peer.cuh"
 
 namespace hlv {

@@ -4,6 +4,8 @@
 // All of these are pure HBM streams (<= 0.5 flop/byte): 128-bit coalesced accesses,
 // several independent loads in flight per thread, persistent grids sized from the SM count,
 // fixed-order reductions with an fp64 final stage (hlv_common.cuh).
+#include <stdlib.h>
+
 #include "hlv_peer.cuh"
 
 namespace hlv {
@@ -530,9 +532,14 @@ static int normalize_store_impl(const char* name, const hlv_peer_ctx* h_ctx, con
     if (peer) HLV_REQUIRE(carve_workspace(ws_raw, ws_bytes, 1, &ws), HLV_ERR_WORKSPACE, "%s: workspace too small", name);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int64_t items = (n / 8 + kThreads * 2 - 1) / (kThreads * 2) + 1;
+    // Peer stores want exactly ONE CTA per SM: measured on 2 x B200 (248 MB to the peer, scripts/dev/peer_store_bench.py) 0.39 ms
+    // = 635 GB/s with 148 CTAs against 0.85 ms with the 592 CTAs of the occupancy-sized grid (and 0.53 ms with 200, 0.57 with 96);
+    // NCCL's all-gather of the same bytes takes 0.58 ms.  Peer LOADS (the reduce-scatter kernel) want the full grid.
+    const int store_grid_cap = (peer && vt.count > 0) ? sm_count() : INT32_MAX;
 #define HLV_NORM_LAUNCH(B, P)                                                                                          \
     do {                                                                                                               \
-        const int grid = persistent_grid(items, resident_ctas(normalize_store_kernel<B, P>));                          \
+        int grid = persistent_grid(items, resident_ctas(normalize_store_kernel<B, P>));                                \
+        if (grid > store_grid_cap) grid = store_grid_cap;                                                              \
         normalize_store_kernel<B, P><<<grid, kThreads, 0, s>>>(w, norm2, n, beta_out, v_out, row_bf16, breakdown_tol,  \
                                                                breakdown_iter, iter, pv, vt, shard_lo, ws.counters);   \
     } while (0)

@@ -256,6 +256,7 @@ class LanczosEngine:
         # kernels over NVLink peer memory (csrc/hlv_peer.cuh)
         self.peer = None
         self.multicast = False
+        self.multicast_store = False
         self.peer_allgather = peer_allgather
         self._v_pending = False
         self.exchange_mode = "none" if G == 1 else "nccl"
@@ -311,9 +312,12 @@ class LanczosEngine:
         #    is nothing to replicate or reduce in the switch).
         mc = os.environ.get("HLV_MULTICAST", "auto")
         self.multicast = bool(peer.hv_multicast and peer.v_multicast) and (mc == "1" or (mc == "auto" and peer.world >= 4))
+        ms = os.environ.get("HLV_MULTICAST_STORE", "auto")     # multimem.st for the v stores, separately from the in-switch add
+        self.multicast_store = bool(peer.v_multicast) and (ms == "1" or (ms == "auto" and self.multicast))
         if self.peer_allgather is None:
             self.peer_allgather = os.environ.get("HLV_PEER_ALLGATHER", "nccl") == "peer"
-        self.exchange_mode = ("peer+multicast" if self.multicast else "peer") + ("" if self.peer_allgather else "+nccl_allgather")
+        self.exchange_mode = (("peer+multicast" if self.multicast else "peer")
+                              + (("+multicast_stores" if self.multicast_store else "+peer_stores") if self.peer_allgather else "+nccl_allgather"))
 
     # -- vectors ---------------------------------------------------------------
     def _v_shard(self, j: int) -> torch.Tensor:
@@ -521,7 +525,7 @@ class LanczosEngine:
                 ops.x_normalize_store(peer, self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16,
                                       peer.v_ptrs if self.peer_allgather else None, self.lo,
                                       self.breakdown_tol, self.breakdown_iter, j, self.ws,
-                                      v_multicast=peer.v_multicast if (self.multicast and self.peer_allgather) else 0)
+                                      v_multicast=peer.v_multicast if (self.multicast_store and self.peer_allgather) else 0)
                 self._v_pending = nxt < self.m and self.peer_allgather
             else:
                 ops.normalize_store(self.w, self.norm2, self.betas[nxt: nxt + 1], v_out, row16,

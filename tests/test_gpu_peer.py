@@ -112,7 +112,7 @@ def test_sharded_engine_over_emulated_peers(cuda_dev, libhlv, world, n, m, reort
     v0 /= v0.norm()
     engs, ctxs = _engines(hlv, world, n, m, cuda_dev, reorth, basis_dtype, parts)
     for e in engs:
-        assert e.exchange_mode == "peer"          # every exchange step inside the kernels (no collective exists in the emulation)
+        assert e.exchange_mode == "peer+peer_stores"          # every exchange step inside the kernels (no collective exists in the emulation)
         e.start(v0)
     for j in range(m):
         emu.lockstep(engs, j)
