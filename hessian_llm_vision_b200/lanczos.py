@@ -304,18 +304,20 @@ class LanczosEngine:
         self.hv_full = peer.hv_full[: self.n_pad]
         self.v_full = peer.v_full[: self.n_pad]
         import os
-        # Measured defaults (8 x B200, profiles/r02_bench_n8_k20_exchange_*.json; knobs for A/B runs):
+        # Measured defaults (profiles/r02_bench_n8_k20_exchange_*.json, r02_bench_n8_k20_ab2_*.json; knobs for A/B runs):
         #  * the reduce-scatter + alpha kernel and the in-kernel coefficient exchange are always used;
-        #  * v_{j+1} is all-gathered by NCCL: its NVLS all-gather (0.73 ms for 8 x 62 MB) beats this library's peer stores
-        #    from the normalise kernel (1.5 ms, unicast or multimem.st alike) -- HLV_PEER_ALLGATHER=peer selects the stores;
-        #  * HLV_MULTICAST=0/1 forces the NVSwitch multicast paths off / on (default: on from 4 ranks -- with one peer there
-        #    is nothing to replicate or reduce in the switch).
+        #  * v_{j+1}: with ONE peer the stores from the normalise kernel (one CTA per SM) move 248 MB in 0.39 ms, NCCL's
+        #    all-gather takes 0.58 ms -> stores at 2 ranks; with 7 peers every thread fans out to 7 destinations and the
+        #    stores drop to 275 GB/s (1.58 ms; multimem.st 1.14 ms) against 0.71 ms for NCCL's NVLS all-gather -> NCCL
+        #    from 3 ranks.  HLV_PEER_ALLGATHER=peer|nccl overrides;
+        #  * HLV_MULTICAST=0/1 forces the in-switch add of the reduce-scatter off / on (default: on from 4 ranks -- with one
+        #    peer there is nothing to reduce in the switch), HLV_MULTICAST_STORE the multimem.st variant of the stores.
         mc = os.environ.get("HLV_MULTICAST", "auto")
         self.multicast = bool(peer.hv_multicast and peer.v_multicast) and (mc == "1" or (mc == "auto" and peer.world >= 4))
         ms = os.environ.get("HLV_MULTICAST_STORE", "auto")     # multimem.st for the v stores, separately from the in-switch add
         self.multicast_store = bool(peer.v_multicast) and (ms == "1" or (ms == "auto" and self.multicast))
         if self.peer_allgather is None:
-            self.peer_allgather = os.environ.get("HLV_PEER_ALLGATHER", "nccl") == "peer"
+            self.peer_allgather = os.environ.get("HLV_PEER_ALLGATHER", "peer" if peer.world == 2 else "nccl") == "peer"
         self.exchange_mode = (("peer+multicast" if self.multicast else "peer")
                               + (("+multicast_stores" if self.multicast_store else "+peer_stores") if self.peer_allgather else "+nccl_allgather"))
 

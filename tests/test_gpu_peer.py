@@ -159,7 +159,7 @@ for name, kw in (("nccl", dict(exchange="nccl")), ("peer", dict(exchange="peer")
                  ("peer_bf16", dict(exchange="peer", basis_dtype=torch.bfloat16)), ("nccl_bf16", dict(exchange="nccl", basis_dtype=torch.bfloat16)),
                  ("peer_noreorth", dict(exchange="peer", reorth=None)), ("nccl_noreorth", dict(exchange="nccl", reorth=None))):
     kw.setdefault("reorth", "full")
-    os.environ["HLV_PEER_ALLGATHER"] = kw.pop("env", "nccl")      # default: NCCL all-gather of v; "peer": stores from the normalise kernel
+    os.environ["HLV_PEER_ALLGATHER"] = kw.pop("env", "nccl")      # "nccl": NCCL all-gather of v; "peer": stores from the normalise kernel
     try:
         eng = hlv.LanczosEngine(lambda q: mine * q, n, m, torch.device("cuda", rank), comm=hlv.Comm(), **kw)
         eng.start(v0)
