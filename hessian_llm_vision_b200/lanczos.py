@@ -19,6 +19,7 @@ kernels on its shard and the partial scalars are combined with k-float all-reduc
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
 
@@ -84,7 +85,6 @@ class _Phases:
     iteration.  The reference only has wall-clock prints around each HVP (gpt2_savehessian.py:178-188)."""
 
     def __init__(self, enabled: bool):
-        import os
         self.enabled = enabled
         self.nvtx = os.environ.get("HLV_NVTX", "0") == "1"
         self.pairs: List[Tuple[str, int, Any, Any]] = []
@@ -303,7 +303,6 @@ class LanczosEngine:
         self.peer = peer
         self.hv_full = peer.hv_full[: self.n_pad]
         self.v_full = peer.v_full[: self.n_pad]
-        import os
         # Measured defaults (profiles/r02_bench_n8_k20_exchange_*.json, r02_bench_n8_k20_ab2_*.json; knobs for A/B runs):
         #  * the reduce-scatter + alpha kernel and the in-kernel coefficient exchange are always used;
         #  * v_{j+1}: with ONE peer the stores from the normalise kernel (one CTA per SM) move 248 MB in 0.39 ms, NCCL's
