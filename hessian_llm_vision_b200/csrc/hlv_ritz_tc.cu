@@ -13,10 +13,10 @@
 // remainder, itself truncated to tf32), D += q_hi*y_hi + q_lo*y_hi + q_hi*y_lo -- error ~2^-21 per product, fp32
 // accumulation in TMEM.
 //
-// Warp roles (576 threads, one CTA per SM, persistent over tiles):
+// Warp roles (320 threads, one CTA per SM, persistent over tiles):
 //   warp 0      TMA producer: one [16 rows x 128 columns] box (8 KB, row-major as in HBM) per stage into a 3-deep ring;
 //               rows >= m arrive as zeros
-//   warps 2-5, 10-13   transpose + split (two groups of four on alternate stages): the contraction runs over the ROWS of the tile, so the A operand must have the basis-row
+//   warps 2-5   transpose + split: the contraction runs over the ROWS of the tile, so the A operand must have the basis-row
 //               index as its K dimension.  Thread t owns column x of the tile = TMEM lane x: it reads its 16 values of the
 //               stage from shared memory (conflict-free scalar loads), splits them into q_hi / q_lo and writes both with
 //               one tcgen05.st each into the A-operand ring IN TENSOR MEMORY (lane = x, 16 columns = the stage's rows) --
@@ -27,9 +27,10 @@
 //               tcgen05.commit frees the operand stage for the split warps; after the last atom of a tile a commit hands the
 //               accumulator to the epilogue.  Also owns the TMEM allocation (512 columns: two 128-column accumulators, so
 //               tile t+1 is multiplied while tile t drains, + 8 operand stages of 32 columns)
-//   warps 6-9, 14-17   epilogue (one group of four per accumulator buffer): tcgen05.ld 32x32b (lane = column x of the tile),
-//               one coalesced 128-byte store per output row
+//   warps 6-9   epilogue: tcgen05.ld 32x32b (lane = column x of the tile), one coalesced 128-byte store per output row
 // Y (hi and lo, zero padded) is staged once per CTA in the same K-major no-swizzle core-matrix layout.
+// Tried and dropped (no gain, profiles/README.md): a second group of split warps and of epilogue warps (18 warps: 21.2 ms per
+// launch under ncu against 19.9 ms for this 10-warp version), the operand in shared memory (SS form: within 3%).
 #include <cuda.h>
 #include <limits.h>
 #include <stdlib.h>
@@ -44,7 +45,7 @@ constexpr int kTcStages = 8;                     // (hi, lo) operand stages IN T
 constexpr int kTcMaxRawStages = 12;              // raw tiles between the TMA producer and the split warps: as many as fit
                                                  // (HBM latency x 44 GB/s per SM wants >= 48 KB of loads in flight per SM)
 constexpr int kTcStageBytes = kTcStageRows * kTcTileCols * 4;        // 8 KB (raw) / 8 KB (hi) + 8 KB (lo)
-constexpr int kTcThreads = 576;                  // 18 warps: producer, MMA issuer, 2 x 4 split warps, 2 x 4 epilogue warps
+constexpr int kTcThreads = 320;
 constexpr int kTcMaxN = 112;
 constexpr int kTcMaxM = 128;
 constexpr int kTcTmemCols = 512;                 // two accumulators of up to 128 columns + the A-operand ring
@@ -250,19 +251,16 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
                 __syncwarp();
             }
         }
-    } else if ((warp >= 2 && warp < 6) || (warp >= 10 && warp < 14)) {
-        // ===== transpose + split warps (two groups of four, on alternate stages: the per-stage chain wait -> 16 loads ->
-        //       split -> tcgen05.st -> wait::st -> arrive is latency-bound, two groups in flight double its throughput): raw [16 rows][128 columns] -> q_hi, q_lo rows of the A operand in TENSOR MEMORY =====
+    } else if (warp < 6) {
+        // ===== transpose + split warps: raw [16 rows][128 columns] -> q_hi, q_lo rows of the A operand in TENSOR MEMORY =====
         // Thread = column x of the tile = TMEM lane (a warp may touch the lane quarter (warp % 4) only): it reads its 16 values
         // of the stage from shared memory (conflict-free), splits them and stores both halves with one tcgen05.st each --
         // the transpose costs nothing, and the MMA reads A from tensor memory instead of shared memory.
         const int x = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTcTmemA;
-        const uint32_t group = warp >= 10 ? 1u : 0u;
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int ks = 0; ks < nstages_per_tile; ++ks, ++it) {
-                if ((it & 1u) != group) continue;
                 const int rs = it % raw_stages, s = it % kTcStages;
                 tc_mbar_wait(&full[rs], (it / raw_stages) & 1u);       // the raw tile has landed
                 const float* src = reinterpret_cast<const float*>(raw + (size_t)rs * kTcStageBytes) + x;
@@ -298,44 +296,35 @@ ritz_vectors_tc_kernel(const __grid_constant__ CUtensorMap tmap, int m, const fl
             }
         }
     } else {
-        // ===== epilogue warps (two groups of four, one per accumulator buffer): TMEM -> registers -> global =====
+        // ===== epilogue warps: TMEM -> registers -> global =====
         const int q = warp & 3;                                        // TMEM lane quarter this warp may read
-        const uint32_t group = warp >= 14 ? 1u : 0u;
         uint32_t tcount = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
             const uint32_t acc = tcount & 1u;
-            if (acc != group) continue;
             tc_mbar_wait(&tmem_full[acc], (tcount >> 1) & 1u);
             tc_fence_after();
             const int64_t x = tile * kTcTileCols + q * 32 + lane;
             const uint32_t taddr = tmem_base + acc * 128u + ((uint32_t)(q * 32) << 16);
             float* dst = out + (int64_t)v0 * ldo + x;
-            // two halves of up to 64 columns: the loads of a half are issued before ONE wait (tcgen05.ld shares the tensor core's
-            // queue with the MMAs of the next tile); stores of full 16-column chunks carry no predicate
+            // every load of the tile is issued before ONE wait (tcgen05.ld shares the tensor core's in-order queue with the MMAs of
+            // the next tile: a wait per chunk would queue behind them again and again); stores of full chunks carry no predicate
+            uint32_t v[kTcMaxN / 16][16];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                if (half * 64 >= n_cols) break;
-                uint32_t v[4][16];
+            for (int k = 0; k < kTcMaxN / 16; ++k)
+                if (k * 16 < n_cols) tc_ld16_nowait(taddr + k * 16, v[k]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&tmem_empty[acc]);          // the accumulator is in registers: the MMA warp may reuse it
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if ((half * 4 + k) * 16 < n_cols) tc_ld16_nowait(taddr + (half * 4 + k) * 16, v[k]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (half == 1 || n_cols <= 64) {                       // the accumulator is in registers: hand it back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc_mbar_arrive(&tmem_empty[acc]);
-                }
+            for (int k = 0; k < kTcMaxN / 16; ++k) {
+                if (k * 16 + 16 <= nvec) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int c = (half * 4 + k) * 16;
-                    if (c + 16 <= nvec) {
+                    for (int j = 0; j < 16; ++j) dst[(int64_t)(k * 16 + j) * ldo] = __uint_as_float(v[k][j]);
+                } else if (k * 16 < nvec) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) dst[(int64_t)(c + j) * ldo] = __uint_as_float(v[k][j]);
-                    } else if (c < nvec) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c + j < nvec) dst[(int64_t)(c + j) * ldo] = __uint_as_float(v[k][j]);
-                    }
+                    for (int j = 0; j < 16; ++j)
+                        if (k * 16 + j < nvec) dst[(int64_t)(k * 16 + j) * ldo] = __uint_as_float(v[k][j]);
                 }
             }
         }
